@@ -1,0 +1,62 @@
+"""Builds libdemon_b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+"""
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_DIR = os.path.join(_HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libdemon_b200.so")
+SOURCES = ["geometry_ops.cu", "conv_simt.cu", "conv_tc.cu", "net.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+
+
+def _deps():
+    out = []
+    for root in (CSRC, os.path.join(_HERE, "..", "include")):
+        for f in os.listdir(root):
+            if f.endswith((".cu", ".cuh", ".h")):
+                out.append(os.path.join(root, f))
+    return out
+
+
+def needs_build():
+    if not os.path.isfile(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(d) > t for d in _deps())
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    os.makedirs(LIB_DIR, exist_ok=True)
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0 or verbose:
+            sys.stderr.write("[nvcc %s]\n%s\n" % (src, out))
+        failed = failed or p.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed")
+    # the driver API (cuTensorMapEncodeTiled) is resolved at run time through cudaGetDriverEntryPoint
+    subprocess.check_call([nvcc, "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,176 @@
+// fp32 CUDA-core implicit-GEMM convolution (NHWC) for sm_100a.
+//
+// Role in the design: (1) the exact-fp32 path for the layers whose shapes do not suit tcgen05 tiles
+// (Cin in {4,6,7,8,9,24}, Cout in {1,2,4,7}, the dense layers) and (2) the on-device fp32 reference
+// the tensor-core path is validated against in tests/.  Classic register-blocked SGEMM structure:
+// 256 threads, a BM x BN output tile (BM*BN = 4096), 4x4 outputs per thread, BK = 16, the A tile
+// gathered on the fly from the NHWC input (zero for padding taps), global loads of tile k+1 in flight
+// while tile k is multiplied out of shared memory.
+#include "conv.cuh"
+
+namespace demon {
+
+namespace {
+
+constexpr int BK = 16;
+
+template <int BM, int BN>
+__global__ void __launch_bounds__(256) conv_simt_kernel(const ConvProblem p) {
+  static_assert(BM * BN == 4096, "256 threads x 16 outputs");
+  constexpr int ROWS_PER_THREAD_LD = BM / 64;   // A-tile float4 loads per thread
+  constexpr int TXN = BN / 4;                   // thread columns
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN];
+
+  const int tid = threadIdx.x;
+  const int M = p.B * p.Ho * p.Wo;
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+
+  // ---- A-load bookkeeping: this thread always loads channel quad `kv` of rows tid/4 + 64*i ------
+  const int kv = tid & 3;
+  int row_n[ROWS_PER_THREAD_LD], row_y[ROWS_PER_THREAD_LD], row_x[ROWS_PER_THREAD_LD];
+#pragma unroll
+  for (int i = 0; i < ROWS_PER_THREAD_LD; ++i) {
+    const int m = m0 + (tid >> 2) + 64 * i;
+    if (m < M) {
+      const int n = m / (p.Ho * p.Wo);
+      const int r = m - n * (p.Ho * p.Wo);
+      const int oy = r / p.Wo;
+      row_n[i] = n; row_y[i] = oy * p.sy; row_x[i] = (r - oy * p.Wo) * p.sx;
+    } else {
+      row_n[i] = -1; row_y[i] = 0; row_x[i] = 0;
+    }
+  }
+  // ---- B-load bookkeeping ---------------------------------------------------------------------
+  const bool b_active = tid < 4 * BN;
+  const int bk = tid / TXN;            // 0..15 when active
+  const int bn = (tid % TXN) * 4;
+
+  const int nchunks = (p.Cin + BK - 1) / BK;
+  const int nk = p.ntaps * nchunks;
+
+  float4 a_reg[ROWS_PER_THREAD_LD];
+  float4 b_reg;
+
+  auto load_global = [&](int it) {
+    const int tap = it / nchunks;
+    const int c0 = (it - tap * nchunks) * BK;
+    const int dy = p.dy[tap], dx = p.dx[tap];
+    const int ci = c0 + kv * 4;
+#pragma unroll
+    for (int i = 0; i < ROWS_PER_THREAD_LD; ++i) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int iy = row_y[i] + dy, ix = row_x[i] + dx;
+      if (row_n[i] >= 0 && ci < p.Cin && iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi)
+        v = __ldg(reinterpret_cast<const float4*>(p.in + ((size_t)(row_n[i] * p.Hi + iy) * p.Wi + ix) * p.in_pitch + ci));
+      a_reg[i] = v;
+    }
+    b_reg = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (b_active && c0 + bk < p.Cin && n0 + bn < p.Cout_pad)
+      b_reg = __ldg(reinterpret_cast<const float4*>(p.w + ((size_t)tap * p.Cin + c0 + bk) * p.Cout_pad + n0 + bn));
+  };
+  auto store_smem = [&]() {
+#pragma unroll
+    for (int i = 0; i < ROWS_PER_THREAD_LD; ++i) {
+      const int r = (tid >> 2) + 64 * i;
+      As[kv * 4 + 0][r] = a_reg[i].x;
+      As[kv * 4 + 1][r] = a_reg[i].y;
+      As[kv * 4 + 2][r] = a_reg[i].z;
+      As[kv * 4 + 3][r] = a_reg[i].w;
+    }
+    if (b_active) *reinterpret_cast<float4*>(&Bs[bk][bn]) = b_reg;
+  };
+
+  const int tx = tid % TXN, ty = tid / TXN;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  load_global(0);
+  store_smem();
+  __syncthreads();
+  for (int it = 0; it < nk; ++it) {
+    if (it + 1 < nk) load_global(it + 1);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+    if (it + 1 < nk) {
+      store_smem();
+      __syncthreads();
+    }
+  }
+
+  // ---- epilogue: bias, leaky ReLU, per-sample scale on channel 0, write into the concat slice ----
+  const int col = n0 + tx * 4;
+  if (col >= p.Cout) return;
+  float bias[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) bias[j] = (col + j < p.Cout_pad) ? __ldg(p.bias + col + j) : 0.f;
+  const bool vec = (col + 3 < p.Cout) && ((p.out_pitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const int n = m / (p.Ho * p.Wo);
+    const int r = m - n * (p.Ho * p.Wo);
+    const int oy = r / p.Wo, ox = r - oy * p.Wo;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x = acc[i][j] + bias[j];
+      if (p.leaky) x = fmaxf(0.1f * x, x);
+      v[j] = x;
+    }
+    if (p.scale != nullptr && col == 0) v[0] *= __ldg(p.scale + (size_t)n * p.scale_stride);
+    float* o = p.out + ((size_t)(n * p.Hfull + oy * p.osy + p.ooy) * p.Wfull + ox * p.osx + p.oox) * p.out_pitch + col;
+    if (vec) {
+      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (col + j < p.Cout) o[j] = v[j];
+    }
+  }
+}
+
+}  // namespace
+
+int conv_simt_launch(const ConvProblem& p, cudaStream_t stream) {
+  DEMON_REQUIRE(p.in && p.out && p.w && p.bias, "conv: null pointer");
+  DEMON_REQUIRE((p.Cin & 3) == 0 && (p.in_pitch & 3) == 0 && (p.Cout_pad & 3) == 0, "conv: Cin (%d), in_pitch (%d), Cout_pad (%d) must be multiples of 4", p.Cin, p.in_pitch, p.Cout_pad);
+  DEMON_REQUIRE((reinterpret_cast<uintptr_t>(p.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.w) & 15) == 0, "conv: in/w must be 16-byte aligned");
+  DEMON_REQUIRE(p.ntaps >= 1 && p.ntaps <= kMaxTaps, "conv: ntaps %d", p.ntaps);
+  const int64_t M = (int64_t)p.B * p.Ho * p.Wo;
+  DEMON_REQUIRE(M < (1ll << 31), "conv: too many output pixels");
+  if (M == 0 || p.Cout == 0) return DEMON_OK;
+  // tile choice: widest N tile that the layer fills
+  if (p.Cout > 32) {
+    dim3 grid(ceil_div((int)M, 64), ceil_div(p.Cout, 64));
+    conv_simt_kernel<64, 64><<<grid, 256, 0, stream>>>(p);
+  } else if (p.Cout > 16) {
+    dim3 grid(ceil_div((int)M, 128), ceil_div(p.Cout, 32));
+    conv_simt_kernel<128, 32><<<grid, 256, 0, stream>>>(p);
+  } else if (p.Cout > 8) {
+    dim3 grid(ceil_div((int)M, 256), ceil_div(p.Cout, 16));
+    conv_simt_kernel<256, 16><<<grid, 256, 0, stream>>>(p);
+  } else {
+    dim3 grid(ceil_div((int)M, 512), ceil_div(p.Cout, 8));
+    conv_simt_kernel<512, 8><<<grid, 256, 0, stream>>>(p);
+  }
+  DEMON_LAUNCH_CHECK();
+  return DEMON_OK;
+}
+
+}  // namespace demon

@@ -1,0 +1,28 @@
+// tcgen05 (5th generation tensor core) implicit-GEMM convolution for sm_100a -- interface.
+#pragma once
+#include "conv.cuh"
+
+namespace demon {
+
+// Per-layer state of the tensor-core path: packed (pre-swizzled, hi/lo split) weights on the device and
+// the TMA tensor map of the input activation slice.
+struct TcLayer {
+  void* w_packed = nullptr;   // device, owned
+  void* tmap_in = nullptr;    // device copy of the CUtensorMap (128 B), owned
+  int n_tile = 0;             // UMMA N of this layer (Cout rounded up to 16)
+  int n_tiles = 0;            // grid.y
+  int k_chunks = 0;           // Cin / 32
+  int th = 0, tw = 0, tb = 0; // output tile: tb images x th rows x tw columns = 128 (or fewer) GEMM rows
+  int nsplit = 3;             // 3 = error-compensated 3xTF32, 1 = plain TF32
+  int stages = 0;
+  int smem_bytes = 0;
+  unsigned char tmap_host[128];
+};
+
+bool tc_layer_supported(const ConvProblem& p);
+// w_host: [ntaps][Cin][Cout_pad] fp32, the same packing the SIMT path uses
+int tc_layer_prepare(TcLayer& t, const ConvProblem& p, const float* w_host, int precision);
+void tc_layer_free(TcLayer& t);
+int conv_tc_launch(const TcLayer& t, const ConvProblem& p, cudaStream_t stream);
+
+}  // namespace demon

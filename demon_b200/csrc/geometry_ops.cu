@@ -1,0 +1,343 @@
+// Standalone geometry ops of the DeMoN hot path (the lmbspecialops ops the network threads between
+// its blocks) as HBM-roofline kernels for sm_100a.  All of them move a few bytes per pixel and do
+// almost no arithmetic, so the design rules are: one thread per (vector of) output pixel(s), the W
+// dimension on threadIdx.x so every warp reads and writes whole 128-byte lines, grids sized from the
+// tensor (they are far larger than 148 SMs at the benchmark sizes), no shared memory except the
+// per-sample camera.
+#include "geometry.cuh"
+
+namespace demon {
+
+std::string& last_error_ref() {
+  static thread_local std::string s;
+  return s;
+}
+std::atomic<int64_t> g_launch_count{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error_ref() = buf;
+  return code;
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp2d  (replaces warp2d.cc:171-256 / warp2d_cuda.cu:31-115)
+// grid (ceil(W/128), H, N), block 128: thread = one output pixel, loops over C like the reference,
+// the displacement is read once per pixel, each channel's four taps are gathers (L1/L2 hits: the
+// displacement field is smooth on the hot path).
+// ---------------------------------------------------------------------------------------------
+template <class T, bool CLAMP>
+__global__ void __launch_bounds__(128) warp2d_kernel(const T* __restrict__ in, const T* __restrict__ disp,
+                                                    T* __restrict__ out, int C, int H, int W,
+                                                    bool normalized, T border_value) {
+  const int x = blockIdx.x * 128 + threadIdx.x;
+  const int y = blockIdx.y;
+  const int n = blockIdx.z;
+  if (x >= W) return;
+  const size_t hw = (size_t)H * W;
+  const T* d = disp + (size_t)n * 2 * hw + (size_t)y * W + x;
+  WarpTap<T> t = warp2d_tap<T>(x, y, __ldg(d), __ldg(d + hw), W, H, normalized);
+  const T* src = in + (size_t)n * C * hw;
+  T* dst = out + (size_t)n * C * hw + (size_t)y * W + x;
+  if (CLAMP) {
+    const int x1i = (int)((unsigned)t.x0 + 1u), y1i = (int)((unsigned)t.y0 + 1u);
+    const int x0 = clampi(t.x0, W), x1 = clampi(x1i, W), y0 = clampi(t.y0, H), y1 = clampi(y1i, H);
+    for (int c = 0; c < C; ++c) {
+      const T* p = src + (size_t)c * hw;
+      T v0 = __ldg(p + (size_t)y0 * W + x0), v1 = __ldg(p + (size_t)y0 * W + x1);
+      T v2 = __ldg(p + (size_t)y1 * W + x0), v3 = __ldg(p + (size_t)y1 * W + x1);
+      dst[(size_t)c * hw] = warp2d_blend(v0, v1, v2, v3, t);
+    }
+  } else {
+    const bool valid = warp2d_valid(t.x0, t.y0, W, H);
+    for (int c = 0; c < C; ++c) {
+      T r = border_value;
+      if (valid) {
+        const T* p = src + (size_t)c * hw + (size_t)t.y0 * W + t.x0;
+        r = warp2d_blend(__ldg(p), __ldg(p + 1), __ldg(p + W), __ldg(p + W + 1), t);
+      }
+      dst[(size_t)c * hw] = r;
+    }
+  }
+}
+
+template <class T>
+static int warp2d_launch(const T* in, const T* disp, T* out, int n, int c, int h, int w, int normalized,
+                         int border_mode, T border_value, void* stream) {
+  DEMON_REQUIRE(in && disp && out, "warp2d: null pointer");
+  DEMON_REQUIRE(n >= 0 && c >= 0 && h >= 0 && w >= 0, "warp2d: negative size");
+  DEMON_REQUIRE(border_mode == DEMON_BORDER_CLAMP || border_mode == DEMON_BORDER_VALUE, "warp2d: border_mode %d", border_mode);
+  if ((int64_t)n * c * h * w == 0) return DEMON_OK;
+  DEMON_REQUIRE(h <= 65535 && n <= 65535, "warp2d: h and n must be <= 65535");
+  dim3 grid(ceil_div(w, 128), h, n), block(128);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (border_mode == DEMON_BORDER_CLAMP)
+    warp2d_kernel<T, true><<<grid, block, 0, s>>>(in, disp, out, c, h, w, normalized != 0, border_value);
+  else
+    warp2d_kernel<T, false><<<grid, block, 0, s>>>(in, disp, out, c, h, w, normalized != 0, border_value);
+  DEMON_LAUNCH_CHECK();
+  return DEMON_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// depth_to_flow (replaces depthtoflow.cc:250-313 / depthtoflow_cuda.cu:62-126 + rotation_format.cu)
+// grid (ceil(HW/256), N): the per-sample camera (Rodrigues etc.) is computed once per CTA by thread 0.
+// ---------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(256) depth_to_flow_kernel(const T* __restrict__ depth, const T* __restrict__ intrinsics,
+                                                           const T* __restrict__ rotation, const T* __restrict__ translation,
+                                                           T* __restrict__ flow, int H, int W, int rotation_format,
+                                                           bool inverse_depth, bool normalize_flow) {
+  __shared__ D2FCamera<T> cam;
+  const int n = blockIdx.y;
+  if (threadIdx.x == 0)
+    d2f_camera(cam, intrinsics + 4 * n, rotation + (size_t)n * rotation_step(rotation_format), translation + 3 * n,
+               rotation_format, W, H);
+  __syncthreads();
+  const int hw = H * W;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= hw) return;
+  const int y = i / W, x = i - y * W;
+  T fx, fy;
+  d2f_pixel(fx, fy, __ldg(depth + (size_t)n * hw + i), x, y, cam, inverse_depth, normalize_flow);
+  flow[(size_t)n * 2 * hw + i] = fx;
+  flow[(size_t)n * 2 * hw + hw + i] = fy;
+}
+
+template <class T>
+static int depth_to_flow_launch(const T* depth, const T* intrinsics, const T* rotation, const T* translation, T* flow,
+                                int n, int h, int w, int rotation_format, int inverse_depth, int normalize_flow, void* stream) {
+  DEMON_REQUIRE(depth && intrinsics && rotation && translation && flow, "depth_to_flow: null pointer");
+  DEMON_REQUIRE(rotation_format >= 0 && rotation_format <= 2, "depth_to_flow: rotation_format %d", rotation_format);
+  DEMON_REQUIRE(n >= 0 && h >= 0 && w >= 0 && n <= 65535, "depth_to_flow: bad size");
+  if ((int64_t)n * h * w == 0) return DEMON_OK;
+  depth_to_flow_kernel<T><<<dim3(ceil_div(h * w, 256), n), 256, 0, (cudaStream_t)stream>>>(
+      depth, intrinsics, rotation, translation, flow, h, w, rotation_format, inverse_depth != 0, normalize_flow != 0);
+  DEMON_LAUNCH_CHECK();
+  return DEMON_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// flow_to_depth / flow_to_depth2 (replaces flowtodepth.cc:383-481; the reference has no GPU kernel)
+// ---------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(128) flow_to_depth_kernel(const T* __restrict__ flow, const T* __restrict__ intrinsics,
+                                                           const T* __restrict__ rotation, const T* __restrict__ translation,
+                                                           T* __restrict__ depth, int H, int W, int rotation_format,
+                                                           bool inverse_depth, bool normalized_flow) {
+  __shared__ F2DCamera<T> cam;
+  const int n = blockIdx.y;
+  if (threadIdx.x == 0)
+    f2d_camera(cam, intrinsics + 4 * n, rotation + (size_t)n * rotation_step(rotation_format), translation + 3 * n,
+               rotation_format, W, H);
+  __syncthreads();
+  const int hw = H * W;
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  if (i >= hw) return;
+  const int y = i / W, x = i - y * W;
+  const T* f = flow + (size_t)n * 2 * hw + i;
+  depth[(size_t)n * hw + i] = f2d_pixel(__ldg(f), __ldg(f + hw), x, y, cam, inverse_depth, normalized_flow);
+}
+
+template <class T>
+static int flow_to_depth_launch(const T* flow, const T* intrinsics, const T* rotation, const T* translation, T* depth,
+                                int n, int h, int w, int rotation_format, int inverse_depth, int normalized_flow, void* stream) {
+  DEMON_REQUIRE(flow && intrinsics && rotation && translation && depth, "flow_to_depth: null pointer");
+  DEMON_REQUIRE(rotation_format >= 0 && rotation_format <= 2, "flow_to_depth: rotation_format %d", rotation_format);
+  DEMON_REQUIRE(n >= 0 && h >= 0 && w >= 0 && n <= 65535, "flow_to_depth: bad size");
+  if ((int64_t)n * h * w == 0) return DEMON_OK;
+  flow_to_depth_kernel<T><<<dim3(ceil_div(h * w, 128), n), 128, 0, (cudaStream_t)stream>>>(
+      flow, intrinsics, rotation, translation, depth, h, w, rotation_format, inverse_depth != 0, normalized_flow != 0);
+  DEMON_LAUNCH_CHECK();
+  return DEMON_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// leaky_relu (replaces leakyrelu.cc:62-82 / leakyrelu_cuda.cu:38-47).  In the networks this op is
+// fused into the convolution epilogues; the standalone kernel exists for API completeness.
+// ---------------------------------------------------------------------------------------------
+template <class T>
+__device__ __forceinline__ T leaky(T x, T leak) {
+  T a = fmul(leak, x);
+  return (a < x) ? x : a;   // std::max(leak*x, x)
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) leaky_relu_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t size, T leak) {
+  constexpr int V = 16 / sizeof(T);
+  struct alignas(16) Vec { T v[V]; };
+  const int64_t nvec = size / V;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (aligned) {
+    for (int64_t j = i; j < nvec; j += stride) {
+      Vec a = reinterpret_cast<const Vec*>(in)[j];
+#pragma unroll
+      for (int k = 0; k < V; ++k) a.v[k] = leaky(a.v[k], leak);
+      reinterpret_cast<Vec*>(out)[j] = a;
+    }
+    for (int64_t j = nvec * V + i; j < size; j += stride) out[j] = leaky(in[j], leak);
+  } else {
+    for (int64_t j = i; j < size; j += stride) out[j] = leaky(in[j], leak);
+  }
+}
+
+template <class T>
+static int leaky_relu_launch(const T* in, T* out, int64_t size, T leak, void* stream) {
+  DEMON_REQUIRE(size >= 0, "leaky_relu: negative size");
+  if (size == 0) return DEMON_OK;
+  DEMON_REQUIRE(in && out, "leaky_relu: null pointer");
+  int64_t blocks = ceil_div64(ceil_div64(size, 16 / sizeof(T)), 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;   // 16 resident CTAs of 256 threads per SM, grid-stride beyond
+  leaky_relu_kernel<T><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, size, leak);
+  DEMON_LAUNCH_CHECK();
+  return DEMON_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// median3x3_downsample (replaces median3x3downsample.cc:112-184 / median3x3downsample_cuda.cu:28-99)
+// grid (ceil(Wo/128), Ho, Z).  Bit exact: comparison only.
+// ---------------------------------------------------------------------------------------------
+template <class T>
+__global__ void __launch_bounds__(128) median3x3_downsample_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                                  int H, int W, int Ho, int Wo, int zbase) {
+  const int xo = blockIdx.x * 128 + threadIdx.x;
+  const int yo = blockIdx.y;
+  const int64_t z = (int64_t)zbase + blockIdx.z;
+  if (xo >= Wo) return;
+  const T* p = in + z * H * W;
+  const int x = 2 * xo, y = 2 * yo;
+  T v[9];
+  int idx = 0;
+#pragma unroll
+  for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+    for (int dx = -1; dx <= 1; ++dx)
+      v[idx++] = __ldg(p + (size_t)clampi(y + dy, H) * W + clampi(x + dx, W));
+  out[z * Ho * Wo + (size_t)yo * Wo + xo] = median9_reference_order(v);
+}
+
+template <class T>
+static int median3x3_launch(const T* in, T* out, int64_t z, int h, int w, void* stream) {
+  DEMON_REQUIRE(z >= 0 && h >= 0 && w >= 0, "median3x3_downsample: negative size");
+  if (z * h * w == 0) return DEMON_OK;
+  DEMON_REQUIRE(in && out, "median3x3_downsample: null pointer");
+  const int ho = (h + 1) / 2, wo = (w + 1) / 2;
+  DEMON_REQUIRE(ho <= 65535, "median3x3_downsample: height too large");
+  for (int64_t z0 = 0; z0 < z; z0 += 32768) {
+    int zn = (int)((z - z0 < 32768) ? (z - z0) : 32768);
+    median3x3_downsample_kernel<T><<<dim3(ceil_div(wo, 128), ho, zn), 128, 0, (cudaStream_t)stream>>>(in, out, h, w, ho, wo, (int)z0);
+    DEMON_LAUNCH_CHECK();
+  }
+  return DEMON_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scale_invariant_gradient forward (replaces scaleinvariantgradient.cc:148-195 /
+// scaleinvariantgradient_cuda.cu:56-102).  deltas/weights travel as kernel arguments (the reference
+// keeps them in a lazily initialised persistent device tensor, scaleinvariantgradient_cuda.cu:241-265).
+// ---------------------------------------------------------------------------------------------
+template <class T>
+struct SigParams {
+  int deltas[16];
+  T weights[16];
+  int num;
+  T eps;
+};
+
+template <class T>
+__global__ void __launch_bounds__(128) sig_kernel(const T* __restrict__ in, T* __restrict__ out, int H, int W, int zbase,
+                                                 SigParams<T> prm) {
+  const int x = blockIdx.x * 128 + threadIdx.x;
+  const int y = blockIdx.y;
+  const int64_t z = (int64_t)zbase + blockIdx.z;
+  if (x >= W) return;
+  const size_t hw = (size_t)H * W;
+  const T* p = in + z * hw;
+  const T v0 = __ldg(p + (size_t)y * W + x);
+  T gx = 0, gy = 0;
+  for (int c = 0; c < prm.num; ++c) {
+    const int d = prm.deltas[c];
+    const T wgt = prm.weights[c];
+    const T vx = (x + d >= 0 && x + d < W) ? __ldg(p + (size_t)y * W + x + d) : v0;
+    const T vy = (y + d >= 0 && y + d < H) ? __ldg(p + (size_t)(y + d) * W + x) : v0;
+    gx = fadd(gx, fdiv(fmul(wgt, fsub(vx, v0)), fadd(fadd(tabs(v0), tabs(vx)), prm.eps)));
+    gy = fadd(gy, fdiv(fmul(wgt, fsub(vy, v0)), fadd(fadd(tabs(v0), tabs(vy)), prm.eps)));
+  }
+  T* o = out + z * 2 * hw + (size_t)y * W + x;
+  o[0] = gx;
+  o[hw] = gy;
+}
+
+template <class T>
+static int sig_launch(const T* in, T* out, int64_t z, int h, int w, const int* deltas, const T* weights, int num, T eps,
+                      void* stream) {
+  DEMON_REQUIRE(z >= 0 && h >= 0 && w >= 0, "scale_invariant_gradient: negative size");
+  DEMON_REQUIRE(num >= 0 && num <= 16, "scale_invariant_gradient: at most 16 deltas (got %d)", num);
+  DEMON_REQUIRE(num == 0 || (deltas && weights), "scale_invariant_gradient: null deltas/weights");
+  if (z * h * w == 0) return DEMON_OK;
+  DEMON_REQUIRE(in && out, "scale_invariant_gradient: null pointer");
+  DEMON_REQUIRE(h <= 65535, "scale_invariant_gradient: height too large");
+  SigParams<T> prm;
+  prm.num = num;
+  prm.eps = eps;
+  for (int i = 0; i < 16; ++i) { prm.deltas[i] = i < num ? deltas[i] : 0; prm.weights[i] = i < num ? weights[i] : (T)0; }
+  for (int64_t z0 = 0; z0 < z; z0 += 32768) {
+    int zn = (int)((z - z0 < 32768) ? (z - z0) : 32768);
+    sig_kernel<T><<<dim3(ceil_div(w, 128), h, zn), 128, 0, (cudaStream_t)stream>>>(in, out, h, w, (int)z0, prm);
+    DEMON_LAUNCH_CHECK();
+  }
+  return DEMON_OK;
+}
+
+}  // namespace demon
+
+using namespace demon;
+
+extern "C" {
+
+const char* demon_last_error(void) { return last_error_ref().c_str(); }
+const char* demon_version(void) { return "demon_b200 0.1 sm_100a"; }
+int64_t demon_launch_count(void) { return g_launch_count.load(); }
+
+int demon_warp2d_f32(const float* i, const float* d, float* o, int n, int c, int h, int w, int nm, int bm, float bv, void* s) {
+  return warp2d_launch<float>(i, d, o, n, c, h, w, nm, bm, bv, s);
+}
+int demon_warp2d_f64(const double* i, const double* d, double* o, int n, int c, int h, int w, int nm, int bm, double bv, void* s) {
+  return warp2d_launch<double>(i, d, o, n, c, h, w, nm, bm, bv, s);
+}
+int demon_depth_to_flow_f32(const float* d, const float* k, const float* r, const float* t, float* f, int n, int h, int w,
+                            int rf, int inv, int nrm, void* s) {
+  return depth_to_flow_launch<float>(d, k, r, t, f, n, h, w, rf, inv, nrm, s);
+}
+int demon_depth_to_flow_f64(const double* d, const double* k, const double* r, const double* t, double* f, int n, int h, int w,
+                            int rf, int inv, int nrm, void* s) {
+  return depth_to_flow_launch<double>(d, k, r, t, f, n, h, w, rf, inv, nrm, s);
+}
+int demon_flow_to_depth_f32(const float* f, const float* k, const float* r, const float* t, float* d, int n, int h, int w,
+                            int rf, int inv, int nrm, void* s) {
+  return flow_to_depth_launch<float>(f, k, r, t, d, n, h, w, rf, inv, nrm, s);
+}
+int demon_flow_to_depth_f64(const double* f, const double* k, const double* r, const double* t, double* d, int n, int h, int w,
+                            int rf, int inv, int nrm, void* s) {
+  return flow_to_depth_launch<double>(f, k, r, t, d, n, h, w, rf, inv, nrm, s);
+}
+int demon_leaky_relu_f32(const float* i, float* o, int64_t size, float leak, void* s) { return leaky_relu_launch<float>(i, o, size, leak, s); }
+int demon_leaky_relu_f64(const double* i, double* o, int64_t size, double leak, void* s) { return leaky_relu_launch<double>(i, o, size, leak, s); }
+int demon_median3x3_downsample_f32(const float* i, float* o, int64_t z, int h, int w, void* s) { return median3x3_launch<float>(i, o, z, h, w, s); }
+int demon_median3x3_downsample_f64(const double* i, double* o, int64_t z, int h, int w, void* s) { return median3x3_launch<double>(i, o, z, h, w, s); }
+int demon_scale_invariant_gradient_f32(const float* i, float* o, int64_t z, int h, int w, const int* d, const float* wt, int num,
+                                       float eps, void* s) {
+  return sig_launch<float>(i, o, z, h, w, d, wt, num, eps, s);
+}
+int demon_scale_invariant_gradient_f64(const double* i, double* o, int64_t z, int h, int w, const int* d, const double* wt, int num,
+                                       double eps, void* s) {
+  return sig_launch<double>(i, o, z, h, w, d, wt, num, eps, s);
+}
+
+}  // extern "C"

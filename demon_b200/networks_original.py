@@ -1,0 +1,259 @@
+"""Mirror of `depthmotionnet.networks_original` (python/depthmotionnet/networks_original.py) over
+the CUDA network plan in libdemon_b200.so.
+
+    session = Session(); session.load_weights(tf_named_weights)        # examples/example.py:70-83
+    bootstrap_net = BootstrapNet(session, data_format)                  # examples/example.py:75-77
+    iterative_net = IterativeNet(session, data_format)
+    refine_net = RefinementNet(session, data_format)
+    result = bootstrap_net.eval(image_pair, image2_2)                   # examples/example.py:87-99
+    ...
+
+Same class names, constructor arguments, `eval` signatures and result-dict keys as the reference;
+numpy (or torch) arrays in, a dict of numpy arrays out (torch CUDA tensors out if the inputs were
+torch CUDA tensors).  `Session` stands in for the `tf.Session` that owns the variables in the
+reference: it owns the TF-named weights and the device network handle.  `DemonPipeline` is the
+fused bootstrap -> N x iterative -> refinement call that never leaves the device.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+PRECISIONS = {"fp32": 0, "3xtf32": 1, "tf32": 2}
+DEFAULT_PRECISION = "3xtf32"
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _NetHandle:
+    """RAII wrapper of a finalized `demon_net*`."""
+
+    def __init__(self, weights, batch, refine_hw, precision):
+        if not torch.cuda.is_available():
+            raise RuntimeError("demon_b200 networks need a CUDA device (there is no CPU fallback)")
+        lib = _lib.load()
+        self._lib = lib
+        self.ptr = ctypes.c_void_p()
+        self.batch, self.refine_hw, self.precision = batch, refine_hw, precision
+        _lib.check(lib.demon_net_create(ctypes.byref(self.ptr), batch, refine_hw[0], refine_hw[1], PRECISIONS[precision]))
+        for i in range(lib.demon_net_num_variables(self.ptr)):
+            name = lib.demon_net_variable_name(self.ptr, i).decode()
+            if name not in weights:
+                raise KeyError("weights are missing variable %r" % name)
+            a = np.ascontiguousarray(weights[name], dtype=np.float32)
+            shape = (ctypes.c_int64 * a.ndim)(*a.shape)
+            _lib.check(lib.demon_net_set_weight(self.ptr, name.encode(), a.ctypes.data_as(ctypes.c_void_p),
+                                                ctypes.cast(shape, ctypes.c_void_p), a.ndim))
+        _lib.check(lib.demon_net_finalize(self.ptr))
+
+    def variable_names(self):
+        return [self._lib.demon_net_variable_name(self.ptr, i).decode()
+                for i in range(self._lib.demon_net_num_variables(self.ptr))]
+
+    def uses_tensor_cores(self, layer):
+        return bool(self._lib.demon_net_layer_uses_tensor_cores(self.ptr, layer.encode()))
+
+    def __del__(self):
+        try:
+            if getattr(self, "ptr", None) is not None and self.ptr.value:
+                self._lib.demon_net_destroy(self.ptr)
+                self.ptr = ctypes.c_void_p()
+        except Exception:
+            pass
+
+
+class Session:
+    """Owner of the variables, in place of the tf.Session of the reference (examples/example.py:70-83)."""
+
+    def __init__(self, precision=DEFAULT_PRECISION):
+        if precision not in PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(PRECISIONS))
+        self.precision = precision
+        self.weights = None
+        self._nets = {}
+
+    def load_weights(self, weights):
+        """weights: dict TF variable name -> numpy array in TF layout (see demon_b200.weights)."""
+        self.weights = weights
+        self._nets = {}
+
+    restore = load_weights
+
+    def net(self, batch, refine_hw=(192, 256)):
+        if self.weights is None:
+            raise RuntimeError("Session.load_weights() has not been called")
+        key = (int(batch), tuple(refine_hw))
+        if key not in self._nets:
+            self._nets[key] = _NetHandle(self.weights, key[0], key[1], self.precision)
+        return self._nets[key]
+
+
+_default_session = None
+
+
+def default_session():
+    global _default_session
+    if _default_session is None:
+        _default_session = Session()
+    return _default_session
+
+
+def _check_format(data_format):
+    if data_format not in ("channels_first", "channels_last"):
+        raise ValueError("data_format must be 'channels_first' or 'channels_last'")
+    return 0 if data_format == "channels_first" else 1
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("demon_b200 networks need a CUDA device (there is no CPU fallback)")
+
+
+def _to_dev(x, shape, name):
+    _require_cuda()
+    was_torch = isinstance(x, torch.Tensor)
+    if was_torch:
+        t = x if x.is_cuda else x.cuda()
+        t = t.to(torch.float32)
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(x), dtype=np.float32)).cuda()
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError("%s: expected shape %s, got %s" % (name, tuple(shape), tuple(t.shape)))
+    return t.contiguous(), (was_torch and x.is_cuda)
+
+
+def _shape(fmt, b, c, h, w):
+    return (b, c, h, w) if fmt == 0 else (b, h, w, c)
+
+
+class _NetBase:
+    def __init__(self, session, data_format="channels_first", batch_size=1):
+        self.session = session if session is not None else default_session()
+        self.data_format = data_format
+        self._fmt = _check_format(data_format)
+        self.batch_size = int(batch_size)
+
+    def _outputs(self, dev):
+        b, f = self.batch_size, self._fmt
+        mk = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        return {
+            "predict_flow5": mk(*_shape(f, b, 2, 6, 8)),
+            "predict_flow2": mk(*_shape(f, b, 2, 48, 64)),
+            "predict_depth2": mk(*_shape(f, b, 1, 48, 64)),
+            "predict_normal2": mk(*_shape(f, b, 3, 48, 64)),
+            "predict_rotation": mk(b, 3),
+            "predict_translation": mk(b, 3),
+        }
+
+    @staticmethod
+    def _finish(out, keep_torch):
+        if keep_torch:
+            return out
+        torch.cuda.current_stream().synchronize()
+        return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+class BootstrapNet(_NetBase):
+    """networks_original.py:22-88."""
+
+    def eval(self, image_pair, image2_2):
+        b, f = self.batch_size, self._fmt
+        ip, t1 = _to_dev(image_pair, _shape(f, b, 6, 192, 256), "image_pair")
+        i2, t2 = _to_dev(image2_2, _shape(f, b, 3, 48, 64), "image2_2")
+        net = self.session.net(b)
+        out = self._outputs(ip.device)
+        _lib.check(_lib.load().demon_bootstrap_forward(
+            net.ptr, ip.data_ptr(), i2.data_ptr(), out["predict_flow5"].data_ptr(), out["predict_flow2"].data_ptr(),
+            out["predict_depth2"].data_ptr(), out["predict_normal2"].data_ptr(), out["predict_rotation"].data_ptr(),
+            out["predict_translation"].data_ptr(), f, _stream()))
+        return self._finish(out, t1 and t2)
+
+
+class IterativeNet(_NetBase):
+    """networks_original.py:92-198.  The intrinsics are the constant of networks_original.py:108."""
+
+    def eval(self, image_pair, image2_2, depth2, normal2, rotation, translation):
+        b, f = self.batch_size, self._fmt
+        ip, t1 = _to_dev(image_pair, _shape(f, b, 6, 192, 256), "image_pair")
+        i2, _ = _to_dev(image2_2, _shape(f, b, 3, 48, 64), "image2_2")
+        d2, _ = _to_dev(depth2, _shape(f, b, 1, 48, 64), "depth2")
+        n2, _ = _to_dev(normal2, _shape(f, b, 3, 48, 64), "normal2")
+        r, _ = _to_dev(rotation, (b, 3), "rotation")
+        t, _ = _to_dev(translation, (b, 3), "translation")
+        net = self.session.net(b)
+        out = self._outputs(ip.device)
+        _lib.check(_lib.load().demon_iterative_forward(
+            net.ptr, ip.data_ptr(), i2.data_ptr(), d2.data_ptr(), n2.data_ptr(), r.data_ptr(), t.data_ptr(),
+            out["predict_flow5"].data_ptr(), out["predict_flow2"].data_ptr(), out["predict_depth2"].data_ptr(),
+            out["predict_normal2"].data_ptr(), out["predict_rotation"].data_ptr(), out["predict_translation"].data_ptr(),
+            f, _stream()))
+        return self._finish(out, t1)
+
+
+class RefinementNet(_NetBase):
+    """networks_original.py:202-255.  `image_size` = (H, W) of image1; the reference fixes (192, 256),
+    the block itself is size generic (blocks_original.py:466-475)."""
+
+    def __init__(self, session, data_format="channels_first", batch_size=1, image_size=(192, 256)):
+        super().__init__(session, data_format, batch_size)
+        self.image_size = (int(image_size[0]), int(image_size[1]))
+        if self.image_size[0] % 4 or self.image_size[1] % 4:
+            raise ValueError("image_size must be a multiple of 4")
+
+    def eval(self, image1, depth2):
+        b, f = self.batch_size, self._fmt
+        H, W = self.image_size
+        im, t1 = _to_dev(image1, _shape(f, b, 3, H, W), "image1")
+        d2, _ = _to_dev(depth2, _shape(f, b, 1, H // 4, W // 4), "depth2")
+        net = self.session.net(b, (H, W))
+        out = {"predict_depth0": torch.empty(_shape(f, b, 1, H, W), dtype=torch.float32, device=im.device)}
+        _lib.check(_lib.load().demon_refine_forward(net.ptr, im.data_ptr(), d2.data_ptr(), out["predict_depth0"].data_ptr(),
+                                                    f, _stream()))
+        return self._finish(out, t1)
+
+
+class DemonPipeline:
+    """examples/example.py:87-99 as one device-resident call (channels_first only)."""
+
+    def __init__(self, session=None, batch_size=1, iterations=3):
+        self.session = session if session is not None else default_session()
+        self.batch_size = int(batch_size)
+        self.iterations = int(iterations)
+        self.net = self.session.net(self.batch_size)
+
+    def forward(self, image_pair, image2_2=None, outputs=None):
+        """image_pair: torch CUDA [B,6,192,256]; image2_2: torch CUDA [B,3,48,64] or None (then it is
+        median3x3_downsample applied twice to the second image, examples/evaluation.py:170-173).
+        Returns dict of torch CUDA tensors; no host synchronisation."""
+        b = self.batch_size
+        ip, _ = _to_dev(image_pair, (b, 6, 192, 256), "image_pair")
+        i2 = None
+        if image2_2 is not None:
+            i2, _ = _to_dev(image2_2, (b, 3, 48, 64), "image2_2")
+        if outputs is None:
+            mk = lambda *s: torch.empty(s, dtype=torch.float32, device=ip.device)
+            outputs = {"predict_depth0": mk(b, 1, 192, 256), "predict_rotation": mk(b, 3), "predict_translation": mk(b, 3),
+                       "predict_flow2": mk(b, 2, 48, 64), "predict_depth2": mk(b, 1, 48, 64), "predict_normal2": mk(b, 3, 48, 64)}
+        ptr = lambda k: outputs[k].data_ptr() if outputs.get(k) is not None else None
+        _lib.check(_lib.load().demon_pipeline_forward(
+            self.net.ptr, ip.data_ptr(), None if i2 is None else i2.data_ptr(), self.iterations,
+            ptr("predict_depth0"), ptr("predict_rotation"), ptr("predict_translation"),
+            ptr("predict_flow2"), ptr("predict_depth2"), ptr("predict_normal2"), _stream()))
+        return outputs
+
+    def forward_host(self, image_pair, image2_2, depth0, rotation, translation):
+        """End-to-end call on HOST buffers (pinned torch CPU tensors or numpy arrays): H2D, pipeline, D2H and a
+        stream synchronise inside the C call."""
+        def hp(x):
+            if x is None:
+                return None
+            return x.data_ptr() if isinstance(x, torch.Tensor) else x.ctypes.data
+        _lib.check(_lib.load().demon_pipeline_forward_host(
+            self.net.ptr, hp(image_pair), hp(image2_2), self.iterations, hp(depth0), hp(rotation), hp(translation), _stream()))
+
+    def launches(self):
+        return _lib.load().demon_net_pipeline_launches(self.net.ptr, self.iterations)

@@ -111,45 +111,48 @@ def variable_specs():
     return out
 
 
-def macs_per_pair():
-    """Algorithmic multiply-accumulates of one image pair through the full
-    pipeline (bootstrap + 3 x iterative + refinement) at 256x192, derived from
-    the layer shapes.  Used for the roofline figure."""
-    def block(specs, res0=(192, 256)):
-        # resolution bookkeeping mirrors the strides in blocks_original.py
-        res = {"conv1y": (96, 256), "conv1x": (96, 128), "conv2y": (48, 128), "conv2x": (48, 64),
-               "conv2_extra_inputsy": (48, 64), "conv2_extra_inputsx": (48, 64),
-               "conv2_1y": (48, 64), "conv2_1x": (48, 64),
-               "conv3y": (24, 64), "conv3x": (24, 32), "conv3_1y": (24, 32), "conv3_1x": (24, 32),
-               "conv4y": (12, 32), "conv4x": (12, 16), "conv4_1y": (12, 16), "conv4_1x": (12, 16),
-               "conv5y": (6, 16), "conv5x": (6, 8), "conv5_1y": (6, 8), "conv5_1x": (6, 8),
-               "predict_flow5/conv1": (6, 8), "predict_flow5/conv2": (6, 8), "motion_conv1": (6, 8),
-               "upsample_flow5to4/upconv": (6, 8), "refine4/upconv": (6, 8), "refine3/upconv": (12, 16),
-               "refine2/upconv": (24, 32),
-               "predict_flow2/conv1": (48, 64), "predict_flow2/conv2": (48, 64),
-               "predict_depthnormal2/conv1": (48, 64), "predict_depthnormal2/conv2": (48, 64)}
-        total = 0
-        for name, kind, shape in specs:
+_TRUNK_RES = {"conv1y": (96, 256), "conv1x": (96, 128), "conv2y": (48, 128), "conv2x": (48, 64),
+              "conv2_extra_inputsy": (48, 64), "conv2_extra_inputsx": (48, 64),
+              "conv2_1y": (48, 64), "conv2_1x": (48, 64),
+              "conv3y": (24, 64), "conv3x": (24, 32), "conv3_1y": (24, 32), "conv3_1x": (24, 32),
+              "conv4y": (12, 32), "conv4x": (12, 16), "conv4_1y": (12, 16), "conv4_1x": (12, 16),
+              "conv5y": (6, 16), "conv5x": (6, 8), "conv5_1y": (6, 8), "conv5_1x": (6, 8),
+              "predict_flow5/conv1": (6, 8), "predict_flow5/conv2": (6, 8), "motion_conv1": (6, 8),
+              "upsample_flow5to4/upconv": (6, 8), "refine4/upconv": (6, 8), "refine3/upconv": (12, 16),
+              "refine2/upconv": (24, 32),
+              "predict_flow2/conv1": (48, 64), "predict_flow2/conv2": (48, 64),
+              "predict_depthnormal2/conv1": (48, 64), "predict_depthnormal2/conv2": (48, 64)}
+
+
+def layer_macs(refine_hw=(192, 256)):
+    """OrderedDict: full layer name ("netFlow1/conv1y") -> algorithmic multiply-accumulates per image pair
+    and per call of that layer.  conv: output pixels x kh x kw x cin x cout; transposed conv: input pixels x
+    16 taps x cin x cout (every input pixel meets every tap once); dense: in x out.  No padding waste, no
+    precision-split multiplier."""
+    h, w = refine_hw
+    refine_res = {"conv0": (h, w), "conv1": (h // 2, w // 2), "conv1_1": (h // 2, w // 2), "conv2": (h // 4, w // 4),
+                  "conv2_1": (h // 4, w // 4), "refine1/upconv": (h // 4, w // 4), "refine0/upconv": (h // 2, w // 2),
+                  "predict_depth0/conv1": (h, w), "predict_depth0/conv2": (h, w)}
+    out = OrderedDict()
+    for scope, fn in SCOPES.items():
+        res = refine_res if scope == "netRefine" else _TRUNK_RES
+        for name, kind, shape in fn():
             if kind == "dense":
-                total += shape[0] * shape[1]
-            elif kind == "deconv":  # MACs counted at the input resolution: every input pixel meets all 16 taps
-                h, w = res[name]
-                total += h * w * shape[0] * shape[1] * shape[2] * shape[3]
-            else:
-                h, w = res[name]
-                total += h * w * shape[0] * shape[1] * shape[2] * shape[3]
-        return total
+                out[scope + "/" + name] = shape[0] * shape[1]
+            else:   # for the transposed convs `res` is the INPUT resolution, for convs the OUTPUT resolution
+                rh, rw = res[name]
+                out[scope + "/" + name] = rh * rw * shape[0] * shape[1] * shape[2] * shape[3]
+    return out
 
-    def refine(h=192, w=256):
-        r = {"conv0": (h, w), "conv1": (h // 2, w // 2), "conv1_1": (h // 2, w // 2), "conv2": (h // 4, w // 4),
-             "conv2_1": (h // 4, w // 4), "refine1/upconv": (h // 4, w // 4), "refine0/upconv": (h // 2, w // 2),
-             "predict_depth0/conv1": (h, w), "predict_depth0/conv2": (h, w)}
-        return sum(r[n][0] * r[n][1] * s[0] * s[1] * s[2] * s[3] for n, _, s in refine_block_specs())
 
-    f1, d1 = block(flow_block_specs(False)), block(depthmotion_block_specs(False))
-    f2, d2 = block(flow_block_specs(True)), block(depthmotion_block_specs(True))
-    return {"netFlow1": f1, "netDM1": d1, "netFlow2": f2, "netDM2": d2, "netRefine": refine(),
-            "pipeline": f1 + d1 + 3 * (f2 + d2) + refine(), "refine_fn": refine}
+def macs_per_pair():
+    """Algorithmic multiply-accumulates of one image pair through the full pipeline (bootstrap + 3 x iterative +
+    refinement) at 256x192: 15 176.3 M = 30.353 GFLOP."""
+    lm = layer_macs()
+    tot = {scope: sum(v for k, v in lm.items() if k.startswith(scope + "/")) for scope in SCOPES}
+    tot["pipeline"] = tot["netFlow1"] + tot["netDM1"] + 3 * (tot["netFlow2"] + tot["netDM2"]) + tot["netRefine"]
+    tot["refine_fn"] = lambda h, w: sum(v for k, v in layer_macs((h, w)).items() if k.startswith("netRefine/"))
+    return tot
 
 
 def synthetic_weights(seed=0, dtype=np.float32):

@@ -1,0 +1,196 @@
+/*
+ * demon_b200 -- C ABI of the B200-native DeMoN two-view inference path.
+ *
+ * This is the drop-in boundary: every entry point replaces one TensorFlow
+ * custom-op kernel (or one `session.run` of a network graph) of the reference
+ * lmb-freiburg/demon.  Plain pointers and sizes only; all tensor pointers are
+ * DEVICE pointers on the current CUDA device unless the name ends in `_host`.
+ * Every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ * performs no allocation and no host synchronisation (the `_host` variants
+ * excepted: they copy in, run, copy out and synchronise the stream), and is
+ * CUDA-graph capturable.
+ *
+ * Return value: 0 on success, a negative DEMON_E_* code otherwise;
+ * demon_last_error() returns a thread-local message for the last failure.
+ *
+ * Layout conventions follow the reference ops: NCHW with all leading
+ * dimensions collapsed by the caller into `n` (warp2d.cc:150-160,
+ * depthtoflow.cc:225-232, flowtodepth.cc:321-328).
+ */
+#ifndef DEMON_B200_H
+#define DEMON_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEMON_OK            0
+#define DEMON_E_INVALID    -1   /* bad argument (shape, enum, null pointer)            */
+#define DEMON_E_CUDA       -2   /* CUDA runtime / driver error (message has the code)  */
+#define DEMON_E_STATE      -3   /* call order (e.g. forward before finalize)           */
+#define DEMON_E_NOTFOUND   -4   /* unknown weight name                                 */
+
+/* enum values shared with the Python layer */
+#define DEMON_BORDER_CLAMP  1   /* warp2d.cc:259 enum BorderMode {CLAMP = 1, VALUE = 2} */
+#define DEMON_BORDER_VALUE  2
+#define DEMON_ROT_MATRIX     0  /* rotation_format.h:27 enum RotationFormat            */
+#define DEMON_ROT_QUATERNION 1
+#define DEMON_ROT_ANGLEAXIS3 2
+
+const char* demon_last_error(void);
+/* "demon_b200 <version> sm_100a" */
+const char* demon_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t demon_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * Geometry ops.  _f32 / _f64 mirror TypeConstraint<float|double>.
+ * ---------------------------------------------------------------------- */
+
+/* Replaces Warp2dOp / warp2d_gpu  (lmbspecialops/src/warp2d.cc:117-273, warp2d_cuda.cu:31-237).
+ * input [n,c,h,w], displacements [n,2,h,w] -> output [n,c,h,w]. */
+int demon_warp2d_f32(const float* input, const float* displacements, float* output,
+                     int n, int c, int h, int w, int normalized, int border_mode,
+                     float border_value, void* stream);
+int demon_warp2d_f64(const double* input, const double* displacements, double* output,
+                     int n, int c, int h, int w, int normalized, int border_mode,
+                     double border_value, void* stream);
+
+/* Replaces DepthToFlowOp (depthtoflow.cc:191-327, depthtoflow_cuda.cu:62-360).
+ * depth [n,h,w], intrinsics [n,4], rotation [n,9|4|3], translation [n,3] -> flow [n,2,h,w]. */
+int demon_depth_to_flow_f32(const float* depth, const float* intrinsics, const float* rotation,
+                            const float* translation, float* flow, int n, int h, int w,
+                            int rotation_format, int inverse_depth, int normalize_flow, void* stream);
+int demon_depth_to_flow_f64(const double* depth, const double* intrinsics, const double* rotation,
+                            const double* translation, double* flow, int n, int h, int w,
+                            int rotation_format, int inverse_depth, int normalize_flow, void* stream);
+
+/* Replaces FlowToDepthOp and FlowToDepth2Op (flowtodepth.cc:284-500, flowtodepth2.cc; CPU-only in
+ * the reference).  flow [n,2,h,w] -> depth [n,1,h,w]. */
+int demon_flow_to_depth_f32(const float* flow, const float* intrinsics, const float* rotation,
+                            const float* translation, float* depth, int n, int h, int w,
+                            int rotation_format, int inverse_depth, int normalized_flow, void* stream);
+int demon_flow_to_depth_f64(const double* flow, const double* intrinsics, const double* rotation,
+                            const double* translation, double* depth, int n, int h, int w,
+                            int rotation_format, int inverse_depth, int normalized_flow, void* stream);
+
+/* Replaces LeakyReluLmbOp (leakyrelu.cc:49-96, leakyrelu_cuda.cu:38-140). */
+int demon_leaky_relu_f32(const float* input, float* output, int64_t size, float leak, void* stream);
+int demon_leaky_relu_f64(const double* input, double* output, int64_t size, double leak, void* stream);
+
+/* Replaces Median3x3DownsampleOp (median3x3downsample.cc:68-197, median3x3downsample_cuda.cu:28-180).
+ * input [z,h,w] -> output [z,ceil(h/2),ceil(w/2)].  Bit exact with the CPU kernel. */
+int demon_median3x3_downsample_f32(const float* input, float* output, int64_t z, int h, int w, void* stream);
+int demon_median3x3_downsample_f64(const double* input, double* output, int64_t z, int h, int w, void* stream);
+
+/* Replaces ScaleInvariantGradientOp forward (scaleinvariantgradient.cc:98-207,
+ * scaleinvariantgradient_cuda.cu:56-102,205-320).  input [z,h,w] -> output [z,2,h,w].
+ * deltas / weights are HOST arrays of length num (<= 16); they are op attributes in the reference. */
+int demon_scale_invariant_gradient_f32(const float* input, float* output, int64_t z, int h, int w,
+                                       const int* deltas, const float* weights, int num, float epsilon,
+                                       void* stream);
+int demon_scale_invariant_gradient_f64(const double* input, double* output, int64_t z, int h, int w,
+                                       const int* deltas, const double* weights, int num, double epsilon,
+                                       void* stream);
+
+/* ------------------------------------------------------------------------
+ * Network graphs (python/depthmotionnet/networks_original.py).
+ * One handle = the five blocks netFlow1, netDM1, netFlow2, netDM2, netRefine for a
+ * fixed batch size at 256x192 (networks_original.py:38-42), plus a refinement block that
+ * is size generic (blocks_original.py:466-475).  All device memory (packed weights,
+ * activation workspace) is allocated in demon_net_create / demon_net_finalize.
+ * ---------------------------------------------------------------------- */
+typedef struct demon_net demon_net;
+
+/* precision of the tensor-core convolution path */
+#define DEMON_PREC_FP32_SIMT  0   /* CUDA-core fp32 FFMA for every layer                           */
+#define DEMON_PREC_3XTF32     1   /* tcgen05 kind::tf32 with error compensation (fp32-grade)       */
+#define DEMON_PREC_TF32       2   /* single-pass tcgen05 kind::tf32 (fast mode, ~1e-3 relative)    */
+
+/* replaces BootstrapNet/IterativeNet/RefinementNet.__init__ (networks_original.py:22-57,92-152,202-234).
+ * refine_h/refine_w: input size of the refinement block (192, 256 for the standard pipeline). */
+int demon_net_create(demon_net** net, int batch, int refine_h, int refine_w, int precision);
+void demon_net_destroy(demon_net* net);
+
+/* replaces tf.train.Saver().restore (examples/example.py:82-83): one call per TF variable,
+ * `name` e.g. "netFlow1/conv1y/kernel"; `data` is a HOST array in TensorFlow's layout
+ * (conv [kh,kw,cin,cout], conv2d_transpose [kh,kw,cout,cin], dense [in,out], bias [cout]). */
+int demon_net_set_weight(demon_net* net, const char* name, const float* data_host,
+                         const int64_t* shape, int rank);
+/* number of variables the graphs need / already set; name of the i-th variable */
+int demon_net_num_variables(const demon_net* net);
+const char* demon_net_variable_name(const demon_net* net, int i);
+/* packs the weights for the device kernels and uploads them; required before any forward */
+int demon_net_finalize(demon_net* net);
+
+/* data_format: 0 = channels_first (NCHW), 1 = channels_last (NHWC) for every image-like tensor */
+
+/* replaces BootstrapNet.eval (networks_original.py:60-88).
+ * image_pair [B,6,192,256], image2_2 [B,3,48,64] ->
+ * flow5 [B,2,6,8], flow2 [B,2,48,64], depth2 [B,1,48,64], normal2 [B,3,48,64], rotation [B,3], translation [B,3] */
+int demon_bootstrap_forward(demon_net* net, const float* image_pair, const float* image2_2,
+                            float* flow5, float* flow2, float* depth2, float* normal2,
+                            float* rotation, float* translation, int data_format, void* stream);
+
+/* replaces IterativeNet.eval (networks_original.py:154-198); same outputs as bootstrap. */
+int demon_iterative_forward(demon_net* net, const float* image_pair, const float* image2_2,
+                            const float* depth2_in, const float* normal2_in,
+                            const float* rotation_in, const float* translation_in,
+                            float* flow5, float* flow2, float* depth2, float* normal2,
+                            float* rotation, float* translation, int data_format, void* stream);
+
+/* replaces RefinementNet.eval (networks_original.py:236-255).
+ * image1 [B,3,H,W], depth2 [B,1,H/4,W/4] -> depth0 [B,1,H,W] */
+int demon_refine_forward(demon_net* net, const float* image1, const float* depth2, float* depth0,
+                         int data_format, void* stream);
+
+/* The whole of examples/example.py:87-99 without leaving the device: bootstrap, `iterations` x
+ * iterative, refinement.  image2_2 may be NULL: it is then computed as
+ * median3x3_downsample(median3x3_downsample(image_pair[:,3:6])) (examples/evaluation.py:170-173).
+ * Any output pointer may be NULL.  channels_first only. */
+int demon_pipeline_forward(demon_net* net, const float* image_pair, const float* image2_2, int iterations,
+                           float* depth0, float* rotation, float* translation,
+                           float* flow2, float* depth2, float* normal2, void* stream);
+
+/* Same, HOST buffers in and out (pinned or pageable): H2D copies, the pipeline, D2H copies and a
+ * stream synchronisation, all inside the call.  This is the end-to-end path bench.py times. */
+int demon_pipeline_forward_host(demon_net* net, const float* image_pair_host, const float* image2_2_host,
+                                int iterations, float* depth0_host, float* rotation_host,
+                                float* translation_host, void* stream);
+
+/* introspection for tests and bench */
+int demon_net_batch(const demon_net* net);
+int64_t demon_net_workspace_bytes(const demon_net* net);
+/* number of kernel launches of one demon_pipeline_forward with `iterations` */
+int demon_net_pipeline_launches(const demon_net* net, int iterations);
+/* 1 if layer `tf_name` (e.g. "netRefine/conv1_1") runs on the tcgen05 path */
+int demon_net_layer_uses_tensor_cores(const demon_net* net, const char* tf_name);
+
+/* Per-layer device timing with CUDA events recorded on the launching stream around every layer of the
+ * forward calls issued between _begin and _end (synchronise the stream before _end).  Used by bench.py for
+ * the roofline figure of the dominant kernel; off by default. */
+int demon_net_profile_begin(demon_net* net);
+int demon_net_profile_end(demon_net* net);
+int demon_net_num_layers(const demon_net* net);
+const char* demon_net_layer_name(const demon_net* net, int i);
+int demon_net_layer_profile(const demon_net* net, int i, double* ms, int64_t* calls, int* launches_per_call,
+                            int* uses_tc);
+
+/* Standalone convolution entry used by tests to compare the tcgen05 path with the fp32 SIMT path on
+ * the same NHWC tensors.  in [B,H,W,Cin], kernel TF layout [kh,kw,cin,cout] (host), bias [cout] (host)
+ * -> out [B,ceil(H/sy),ceil(W/sx),Cout]; caffe padding (helpers.py:70-94). */
+int demon_conv2d_nhwc(const float* in, float* out, int B, int H, int W, int Cin, int Cout,
+                      int kh, int kw, int sy, int sx, const float* kernel_host, const float* bias_host,
+                      int leaky, int precision, void* stream);
+/* conv2d_transpose k4 s2 (blocks_original.py:97-110): in [B,H,W,Cin], kernel [4,4,cout,cin] (host)
+ * -> out [B,2H,2W,Cout] */
+int demon_deconv4x4s2_nhwc(const float* in, float* out, int B, int H, int W, int Cin, int Cout,
+                           const float* kernel_host, const float* bias_host, int leaky, int precision,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEMON_B200_H */

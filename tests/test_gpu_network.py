@@ -1,0 +1,247 @@
+"""GPU: the network graphs through the C ABI (via the networks_original mirror) against the CPU oracle.
+
+The north-star bar: inverse-depth L1-rel <= 1e-4 on predict_depth0 and flow EPE <= 1e-4 on predict_flow2
+(normalized units), measured against the fp32 CPU oracle; the fp64 oracle distance is checked too."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from demon_b200 import weights as W
+from oracle import ops as oops
+from oracle.network import OracleNets
+
+TOL = 1e-4
+
+
+def l1_rel(a, r):
+    """l1 relative error on inverse depth (python/depthmotionnet/evaluation/metrics.py:62-81,151-170 family)."""
+    return float(np.abs(a - r).sum() / np.abs(r).sum())
+
+
+def epe(a, r):
+    """compute_flow_epe, python/depthmotionnet/evaluation/metrics.py:377-387."""
+    return float(np.sqrt(((a - r) ** 2).sum(axis=1)).mean())
+
+
+def demeaned_rel(a, r):
+    """stricter: error relative to the spatially varying part of the signal"""
+    return float(np.abs(a - r).sum() / np.abs(r - r.mean()).sum())
+
+
+@pytest.fixture(scope="module")
+def sessions(synthetic_weights):
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+    from demon_b200.networks_original import Session
+    out = {}
+    for prec in ("fp32", "3xtf32"):
+        s = Session(precision=prec)
+        s.load_weights(synthetic_weights)
+        out[prec] = s
+    return out
+
+
+@pytest.fixture(scope="module")
+def oracle32(synthetic_weights):
+    return OracleNets(synthetic_weights)
+
+
+@pytest.fixture(scope="module")
+def random_pairs():
+    g = torch.Generator().manual_seed(1234)      # SURVEY.md section 8d config 3 generator
+    ip = (torch.rand(2, 6, 192, 256, generator=g) - 0.5).numpy()
+    i22 = oops.median3x3_downsample(oops.median3x3_downsample(np.ascontiguousarray(ip[:, 3:6])))
+    return ip, i22
+
+
+def test_variable_table_agrees_with_python_table(sessions):
+    net = sessions["fp32"].net(1)
+    assert net.variable_names() == list(W.variable_specs().keys())
+
+
+def test_tensor_core_path_is_selected_for_the_big_layers(sessions):
+    net = sessions["3xtf32"].net(1)
+    for layer in ("netRefine/conv1_1", "netFlow1/conv3x", "netDM2/refine3/upconv", "netRefine/refine0/upconv"):
+        assert net.uses_tensor_cores(layer), layer
+    for layer in ("netFlow1/conv1y", "netDM1/motion_fc1", "netRefine/predict_depth0/conv2"):
+        assert not net.uses_tensor_cores(layer), layer
+    assert not sessions["fp32"].net(1).uses_tensor_cores("netRefine/conv1_1")
+
+
+@pytest.mark.parametrize("prec", ("fp32", "3xtf32"))
+def test_bootstrap_on_sculpture_pair(sessions, oracle32, sculpture, prec):
+    """BASELINE.json configs[1], first stage."""
+    from demon_b200.networks_original import BootstrapNet
+    out = BootstrapNet(sessions[prec], "channels_first", 1).eval(sculpture["image_pair"], sculpture["image2_2"])
+    ref = oracle32.bootstrap(sculpture["image_pair"], sculpture["image2_2"])
+    assert set(out) == {"predict_flow5", "predict_flow2", "predict_depth2", "predict_normal2", "predict_rotation", "predict_translation"}
+    for k in out:
+        assert out[k].shape == tuple(ref[k].shape), k
+    assert epe(out["predict_flow2"], ref["predict_flow2"].numpy()) < TOL
+    assert epe(out["predict_flow5"], ref["predict_flow5"].numpy()) < TOL
+    assert l1_rel(out["predict_depth2"], ref["predict_depth2"].numpy()) < TOL
+    np.testing.assert_allclose(out["predict_normal2"], ref["predict_normal2"].numpy(), atol=1e-4)
+    np.testing.assert_allclose(out["predict_rotation"], ref["predict_rotation"].numpy(), atol=1e-5)
+    np.testing.assert_allclose(out["predict_translation"], ref["predict_translation"].numpy(), atol=1e-5)
+
+
+@pytest.mark.parametrize("prec", ("fp32", "3xtf32"))
+def test_iterative_and_refine_stage_by_stage(sessions, oracle32, random_pairs, prec):
+    """Each eval() fed with the ORACLE's previous outputs: isolates every stage (networks_original.py:154-255)."""
+    from demon_b200.networks_original import IterativeNet, RefinementNet
+    ip, i22 = random_pairs
+    r0 = oracle32.bootstrap(ip, i22)
+    args = (ip, i22, r0["predict_depth2"].numpy(), r0["predict_normal2"].numpy(), r0["predict_rotation"].numpy(),
+            r0["predict_translation"].numpy())
+    out = IterativeNet(sessions[prec], "channels_first", 2).eval(*args)
+    ref = oracle32.iterative(*args)
+    assert epe(out["predict_flow2"], ref["predict_flow2"].numpy()) < TOL
+    assert l1_rel(out["predict_depth2"], ref["predict_depth2"].numpy()) < TOL
+    np.testing.assert_allclose(out["predict_rotation"], ref["predict_rotation"].numpy(), atol=1e-5)
+    np.testing.assert_allclose(out["predict_translation"], ref["predict_translation"].numpy(), atol=1e-5)
+    image1 = np.ascontiguousarray(ip[:, 0:3])
+    d2 = ref["predict_depth2"].numpy()
+    o = RefinementNet(sessions[prec], "channels_first", 2).eval(image1, d2)
+    r = oracle32.refine(image1, d2)
+    assert o["predict_depth0"].shape == (2, 1, 192, 256)
+    assert l1_rel(o["predict_depth0"], r["predict_depth0"].numpy()) < TOL
+    assert demeaned_rel(o["predict_depth0"], r["predict_depth0"].numpy()) < 10 * TOL
+
+
+def test_channels_last_equals_channels_first(sessions, random_pairs):
+    """data_format is a pure boundary transpose (networks_original.py:37-42)."""
+    from demon_b200.networks_original import BootstrapNet, RefinementNet
+    ip, i22 = random_pairs
+    s = sessions["3xtf32"]
+    a = BootstrapNet(s, "channels_first", 2).eval(ip, i22)
+    b = BootstrapNet(s, "channels_last", 2).eval(np.ascontiguousarray(ip.transpose(0, 2, 3, 1)), np.ascontiguousarray(i22.transpose(0, 2, 3, 1)))
+    assert b["predict_flow2"].shape == (2, 48, 64, 2) and b["predict_normal2"].shape == (2, 48, 64, 3)
+    for k in ("predict_flow5", "predict_flow2", "predict_depth2", "predict_normal2"):
+        assert np.array_equal(a[k], b[k].transpose(0, 3, 1, 2)), k
+    assert np.array_equal(a["predict_rotation"], b["predict_rotation"])
+    image1 = np.ascontiguousarray(ip[:, 0:3])
+    ra = RefinementNet(s, "channels_first", 2).eval(image1, a["predict_depth2"])
+    rb = RefinementNet(s, "channels_last", 2).eval(np.ascontiguousarray(image1.transpose(0, 2, 3, 1)), b["predict_depth2"])
+    assert np.array_equal(ra["predict_depth0"], rb["predict_depth0"].transpose(0, 3, 1, 2))
+
+
+@pytest.mark.parametrize("prec", ("fp32", "3xtf32"))
+def test_full_pipeline_against_oracle_and_golden(sessions, oracle32, sculpture, golden_dir, prec):
+    """BASELINE.json configs[1]: full pipeline batch 1 on the sculpture pair vs the CPU path, and vs the
+    committed golden outputs (fp32 and fp64 oracle)."""
+    from demon_b200.networks_original import DemonPipeline
+    pipe = DemonPipeline(sessions[prec], batch_size=1, iterations=3)
+    out = pipe.forward(torch.from_numpy(sculpture["image_pair"]).cuda(), torch.from_numpy(sculpture["image2_2"]).cuda())
+    torch.cuda.synchronize()
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    g = np.load(os.path.join(golden_dir, "oracle_pipeline.npz"))
+    for sfx in ("_f32", "_f64"):
+        assert l1_rel(out["predict_depth0"], g["predict_depth0" + sfx]) < TOL
+        assert epe(out["predict_flow2"], g["predict_flow2" + sfx]) < TOL
+        assert l1_rel(out["predict_depth2"], g["predict_depth2" + sfx]) < TOL
+        np.testing.assert_allclose(out["predict_rotation"], g["predict_rotation" + sfx], atol=1e-5)
+        np.testing.assert_allclose(out["predict_translation"], g["predict_translation" + sfx], atol=1e-5)
+    print("\n[%s] depth0 L1-rel vs fp64 oracle %.3e (de-meaned %.3e), flow EPE %.3e" % (
+        prec, l1_rel(out["predict_depth0"], g["predict_depth0_f64"]), demeaned_rel(out["predict_depth0"], g["predict_depth0_f64"]),
+        epe(out["predict_flow2"], g["predict_flow2_f64"])))
+    assert pipe.launches() > 0
+
+
+def test_pipeline_matches_stagewise_api_and_median_image2_2(sessions, random_pairs):
+    """The fused pipeline == the five eval() calls of examples/example.py:87-99, bit for bit; image2_2=None
+    reproduces median3x3_downsample twice (examples/evaluation.py:170-173)."""
+    from demon_b200.networks_original import BootstrapNet, IterativeNet, RefinementNet, DemonPipeline
+    ip, i22 = random_pairs
+    s = sessions["3xtf32"]
+    r = BootstrapNet(s, "channels_first", 2).eval(ip, i22)
+    it = IterativeNet(s, "channels_first", 2)
+    for _ in range(3):
+        r = it.eval(ip, i22, r["predict_depth2"], r["predict_normal2"], r["predict_rotation"], r["predict_translation"])
+    d0 = RefinementNet(s, "channels_first", 2).eval(np.ascontiguousarray(ip[:, 0:3]), r["predict_depth2"])["predict_depth0"]
+    pipe = DemonPipeline(s, batch_size=2, iterations=3)
+    out = pipe.forward(torch.from_numpy(ip).cuda(), None)
+    torch.cuda.synchronize()
+    assert np.array_equal(out["predict_depth0"].cpu().numpy(), d0)
+    assert np.array_equal(out["predict_flow2"].cpu().numpy(), r["predict_flow2"])
+    assert np.array_equal(out["predict_rotation"].cpu().numpy(), r["predict_rotation"])
+    # host-buffer entry (the e2e path of bench.py)
+    hp = torch.from_numpy(ip).pin_memory()
+    d0h = torch.empty(2, 1, 192, 256).pin_memory()
+    rot, tr = torch.empty(2, 3).pin_memory(), torch.empty(2, 3).pin_memory()
+    pipe.forward_host(hp, None, d0h, rot, tr)
+    assert np.array_equal(d0h.numpy(), d0) and np.array_equal(rot.numpy(), r["predict_rotation"])
+
+
+def test_batch_consistency_and_determinism_at_benchmark_batch(sessions, synthetic_weights):
+    """BASELINE.json configs[2] size (batch 64): every sample equals the batch-1 result of the same pair
+    (pairs are independent, blocks_original.py has no cross-sample op), two runs are bit identical, and a
+    sample checked against the CPU oracle is inside the tolerance."""
+    from demon_b200.networks_original import DemonPipeline
+    g = torch.Generator().manual_seed(1234)
+    ip = (torch.rand(64, 6, 192, 256, generator=g) - 0.5)
+    s = sessions["3xtf32"]
+    pipe = DemonPipeline(s, batch_size=64, iterations=3)
+    x = ip.cuda()
+    a = {k: v.clone() for k, v in pipe.forward(x, None).items()}
+    b = pipe.forward(x, None)
+    torch.cuda.synchronize()
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+        assert torch.isfinite(a[k]).all(), k
+    one = DemonPipeline(s, batch_size=1, iterations=3)
+    for i in (0, 37, 63):
+        o = one.forward(x[i:i + 1], None)
+        torch.cuda.synchronize()
+        assert torch.equal(o["predict_depth0"][0], a["predict_depth0"][i]), i
+        assert torch.equal(o["predict_translation"][0], a["predict_translation"][i]), i
+    i = 37
+    ipn = ip[i:i + 1].numpy()
+    i22 = oops.median3x3_downsample(oops.median3x3_downsample(np.ascontiguousarray(ipn[:, 3:6])))
+    ref = OracleNets(synthetic_weights).pipeline(ipn, i22)
+    assert l1_rel(a["predict_depth0"][i:i + 1].cpu().numpy(), ref["predict_depth0"].numpy()) < TOL
+    assert epe(a["predict_flow2"][i:i + 1].cpu().numpy(), ref["predict_flow2"].numpy()) < TOL
+
+
+def test_adversarial_weights_exercise_invalid_geometry_branches(synthetic_weights):
+    """Negative / zero inverse depths and a large motion: depth_to_flow yields NaN, the |flow| < 1 gate
+    (blocks_original.py:165-168) zeroes it, flow_to_depth returns 0 behind the camera.  Outputs must stay
+    finite and match the oracle."""
+    from demon_b200.networks_original import Session, DemonPipeline
+    w = dict(synthetic_weights)
+    for scope in ("netDM1", "netDM2"):
+        w[scope + "/predict_depthnormal2/conv2/bias"] = np.array([0.0, 0, 0, -0.8], np.float32)      # depth straddles 0
+        w[scope + "/predict_depthnormal2/conv2/kernel"] = synthetic_weights[scope + "/predict_depthnormal2/conv2/kernel"] * 5
+        w[scope + "/motion_fc3/bias"] = np.array([0.3, -0.2, 0.1, 2.5, 0.5, -0.7, 1.0], np.float32)  # large motion
+    s = Session("3xtf32")
+    s.load_weights(w)
+    g = torch.Generator().manual_seed(99)
+    ip = (torch.rand(1, 6, 192, 256, generator=g) - 0.5).numpy()
+    i22 = oops.median3x3_downsample(oops.median3x3_downsample(np.ascontiguousarray(ip[:, 3:6])))
+    orc = OracleNets(w)
+    r0 = orc.bootstrap(ip, i22)
+    assert (r0["predict_depth2"].numpy() <= 0).mean() > 0.05
+    ref_it = orc.iterative(ip, i22, r0["predict_depth2"], r0["predict_normal2"], r0["predict_rotation"], r0["predict_translation"], full=True)
+    assert (ref_it["flow_from_depth_motion"].numpy() == 0).mean() > 0.05       # gated pixels
+    assert (ref_it["depth_from_flow"].numpy() == 0).mean() > 0.001            # behind-camera pixels
+    out = DemonPipeline(s, 1, 3).forward(torch.from_numpy(ip).cuda(), torch.from_numpy(i22).cuda())
+    torch.cuda.synchronize()
+    ref = orc.pipeline(ip, i22)
+    d = out["predict_depth0"].cpu().numpy()
+    assert np.isfinite(d).all()
+    assert l1_rel(d, ref["predict_depth0"].numpy()) < 10 * TOL     # threshold flips of single pixels are allowed to show
+    assert epe(out["predict_flow2"].cpu().numpy(), ref["predict_flow2"].numpy()) < 10 * TOL
+
+
+def test_refinement_at_1024x768(sessions, synthetic_weights):
+    """BASELINE.json configs[4]: RefinementNet at 1024x768, batch 2 here (the oracle takes ~10 s per image)."""
+    from demon_b200.networks_original import RefinementNet
+    rng = np.random.RandomState(4)
+    image1 = rng.uniform(-0.5, 0.5, (1, 3, 768, 1024)).astype(np.float32)
+    depth2 = rng.uniform(0.2, 0.8, (1, 1, 192, 256)).astype(np.float32)
+    o = RefinementNet(sessions["3xtf32"], "channels_first", 1, image_size=(768, 1024)).eval(image1, depth2)
+    r = OracleNets(synthetic_weights).refine(image1, depth2)
+    assert o["predict_depth0"].shape == (1, 1, 768, 1024)
+    assert l1_rel(o["predict_depth0"], r["predict_depth0"].numpy()) < TOL
