@@ -24,5 +24,7 @@ bool tc_layer_supported(const ConvProblem& p);
 int tc_layer_prepare(TcLayer& t, const ConvProblem& p, const float* w_host, int precision);
 void tc_layer_free(TcLayer& t);
 int conv_tc_launch(const TcLayer& t, const ConvProblem& p, cudaStream_t stream);
+// 1 if any mbarrier wait of the tcgen05 kernel has timed out since process start (pipeline bug detector)
+int tc_read_error_flag();
 
 }  // namespace demon

@@ -143,35 +143,41 @@ __device__ __forceinline__ void d2f_pixel(T& fvx, T& fvy, T d, int x, int y, con
 }
 
 // ---- flow_to_depth: per-sample projection matrices, flowtodepth.cc:402-419 --------------------
-template <class T>
+// Everything from here to the solved point is carried in DOUBLE, for both T = float and T = double.  The
+// triangulation is ill conditioned wherever the flow is close to the infinite-depth flow (cond(A) reaches 1e5 on
+// the flows the network produces), so each float rounding -- of R, of K*[R|t], of the rows of A -- moves the
+// result by cond * 6e-8, i.e. up to 1e-3 relative on those pixels.  The reference's float path has exactly that
+// noise (its own realisation of it: Eigen's JacobiSVD); carrying double here puts this kernel at the exact
+// solution for the given float inputs, which is the closest any implementation can be to every float realisation.
 struct F2DCamera {
-  T P1[3][4];
-  T P2[3][4];
-  T inv_w, inv_h;
+  double P1[3][4];
+  double P2[3][4];
+  double inv_w, inv_h;
 };
 
 template <class T>
-__device__ void f2d_camera(F2DCamera<T>& cam, const T* intrinsics, const T* rotation, const T* translation,
+__device__ void f2d_camera(F2DCamera& cam, const T* intrinsics, const T* rotation, const T* translation,
                            int rotation_format, int w, int h) {
-  T K[9] = {intrinsics[0], 0, intrinsics[2], 0, intrinsics[1], intrinsics[3], 0, 0, 1};
-  T R[9];
-  to_rotation_matrix(R, rotation, rotation_format);
-  T Rt[3][4];
+  const double K[9] = {(double)intrinsics[0], 0, (double)intrinsics[2], 0, (double)intrinsics[1], (double)intrinsics[3], 0, 0, 1};
+  double rd[9], R[9];
+  const int step = rotation_step(rotation_format);
+  for (int i = 0; i < step; ++i) rd[i] = (double)rotation[i];
+  to_rotation_matrix<double>(R, rd, rotation_format);
+  double Rt[3][4];
   for (int i = 0; i < 3; ++i) {
     for (int j = 0; j < 3; ++j) { cam.P1[i][j] = K[3 * i + j]; Rt[i][j] = R[3 * i + j]; }
-    cam.P1[i][3] = 0; Rt[i][3] = translation[i];
+    cam.P1[i][3] = 0; Rt[i][3] = (double)translation[i];
   }
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 4; ++j)
       cam.P2[i][j] = fadd(fadd(fmul(K[3 * i + 0], Rt[0][j]), fmul(K[3 * i + 1], Rt[1][j])), fmul(K[3 * i + 2], Rt[2][j]));
-  cam.inv_w = (T)(1.0 / w); cam.inv_h = (T)(1.0 / h);
+  cam.inv_w = 1.0 / w; cam.inv_h = 1.0 / h;
 }
 
 // Least squares argmin |A X - b| for the 4x3 system of triangulateLinear (flowtodepth.cc:251-281).
-// The reference calls Eigen's JacobiSVD in precision T on a heap-allocated dynamic matrix.  Here: the
-// system is assembled in T exactly like the reference, then solved by Householder QR in double -- a
-// backward-stable solver whose error (cond(A) * 1e-16) is far below the float SVD's own
-// (cond(A) * 6e-8), so the result is the reference's up to the reference's rounding noise.
+// The reference calls Eigen's JacobiSVD in precision T on a heap-allocated dynamic matrix.  Here: Householder
+// QR in double -- backward stable, error cond(A) * 1e-16, so the result is the exact least-squares solution
+// to float output precision.
 // Rank deficiency shows up as a zero pivot -> non-finite X -> output 0, the same value the reference
 // produces through its minimum-norm solution (X.z = 0 fails `X.z() > 0`, flowtodepth.cc:464).
 __device__ __forceinline__ void lsq_4x3_qr(double X[3], double A[4][3], double b[4]) {
@@ -211,30 +217,31 @@ __device__ __forceinline__ void lsq_4x3_qr(double X[3], double A[4][3], double b
   X[0] = (b[0] - A[0][1] * X[1] - A[0][2] * X[2]) / A[0][0];
 }
 
-// flowtodepth.cc:430-474 for one pixel
+// flowtodepth.cc:430-474 for one pixel: rows of A and b as in triangulateLinear (flowtodepth.cc:261-273)
 template <class T>
-__device__ __forceinline__ T f2d_pixel(T fx_, T fy_, int x, int y, const F2DCamera<T>& cam,
+__device__ __forceinline__ T f2d_pixel(T fx_, T fy_, int x, int y, const F2DCamera& cam,
                                        bool inverse_depth, bool normalized_flow) {
-  T x1x = fmul(fadd((T)x, (T)0.5), cam.inv_w), x1y = fmul(fadd((T)y, (T)0.5), cam.inv_h);
-  if (!normalized_flow) { fx_ = fmul(fx_, cam.inv_w); fy_ = fmul(fy_, cam.inv_h); }
-  T x2x = fadd(x1x, fx_), x2y = fadd(x1y, fy_);
+  const double x1x = (x + 0.5) * cam.inv_w, x1y = (y + 0.5) * cam.inv_h;
+  double fx = (double)fx_, fy = (double)fy_;
+  if (!normalized_flow) { fx *= cam.inv_w; fy *= cam.inv_h; }
+  const double x2x = x1x + fx, x2y = x1y + fy;
   double A[4][3], b[4];
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    A[0][j] = (double)fsub(fmul(x1y, cam.P1[2][j]), cam.P1[1][j]);
-    A[1][j] = (double)fsub(cam.P1[0][j], fmul(x1x, cam.P1[2][j]));
-    A[2][j] = (double)fsub(fmul(x2y, cam.P2[2][j]), cam.P2[1][j]);
-    A[3][j] = (double)fsub(cam.P2[0][j], fmul(x2x, cam.P2[2][j]));
+    A[0][j] = x1y * cam.P1[2][j] - cam.P1[1][j];
+    A[1][j] = cam.P1[0][j] - x1x * cam.P1[2][j];
+    A[2][j] = x2y * cam.P2[2][j] - cam.P2[1][j];
+    A[3][j] = cam.P2[0][j] - x2x * cam.P2[2][j];
   }
-  b[0] = (double)fsub(cam.P1[1][3], fmul(x1y, cam.P1[2][3]));
-  b[1] = (double)fsub(fmul(x1x, cam.P1[2][3]), cam.P1[0][3]);
-  b[2] = (double)fsub(cam.P2[1][3], fmul(x2y, cam.P2[2][3]));
-  b[3] = (double)fsub(fmul(x2x, cam.P2[2][3]), cam.P2[0][3]);
+  b[0] = cam.P1[1][3] - x1y * cam.P1[2][3];
+  b[1] = x1x * cam.P1[2][3] - cam.P1[0][3];
+  b[2] = cam.P2[1][3] - x2y * cam.P2[2][3];
+  b[3] = x2x * cam.P2[2][3] - cam.P2[0][3];
   double X[3];
   lsq_4x3_qr(X, A, b);
   T Xx = (T)X[0], Xy = (T)X[1], Xz = (T)X[2];
   if (isfinite(Xx) && isfinite(Xy) && isfinite(Xz) && Xz > 0)
-    return inverse_depth ? fdiv((T)1, Xz) : Xz;
+    return inverse_depth ? (T)(1.0 / X[2]) : Xz;
   return (T)0;
 }
 

@@ -68,10 +68,10 @@ __global__ void __launch_bounds__(128) warp2d_kernel(const T* __restrict__ in, c
 template <class T>
 static int warp2d_launch(const T* in, const T* disp, T* out, int n, int c, int h, int w, int normalized,
                          int border_mode, T border_value, void* stream) {
-  DEMON_REQUIRE(in && disp && out, "warp2d: null pointer");
   DEMON_REQUIRE(n >= 0 && c >= 0 && h >= 0 && w >= 0, "warp2d: negative size");
   DEMON_REQUIRE(border_mode == DEMON_BORDER_CLAMP || border_mode == DEMON_BORDER_VALUE, "warp2d: border_mode %d", border_mode);
   if ((int64_t)n * c * h * w == 0) return DEMON_OK;
+  DEMON_REQUIRE(in && disp && out, "warp2d: null pointer");
   DEMON_REQUIRE(h <= 65535 && n <= 65535, "warp2d: h and n must be <= 65535");
   dim3 grid(ceil_div(w, 128), h, n), block(128);
   cudaStream_t s = (cudaStream_t)stream;
@@ -111,10 +111,10 @@ __global__ void __launch_bounds__(256) depth_to_flow_kernel(const T* __restrict_
 template <class T>
 static int depth_to_flow_launch(const T* depth, const T* intrinsics, const T* rotation, const T* translation, T* flow,
                                 int n, int h, int w, int rotation_format, int inverse_depth, int normalize_flow, void* stream) {
-  DEMON_REQUIRE(depth && intrinsics && rotation && translation && flow, "depth_to_flow: null pointer");
   DEMON_REQUIRE(rotation_format >= 0 && rotation_format <= 2, "depth_to_flow: rotation_format %d", rotation_format);
   DEMON_REQUIRE(n >= 0 && h >= 0 && w >= 0 && n <= 65535, "depth_to_flow: bad size");
   if ((int64_t)n * h * w == 0) return DEMON_OK;
+  DEMON_REQUIRE(depth && intrinsics && rotation && translation && flow, "depth_to_flow: null pointer");
   depth_to_flow_kernel<T><<<dim3(ceil_div(h * w, 256), n), 256, 0, (cudaStream_t)stream>>>(
       depth, intrinsics, rotation, translation, flow, h, w, rotation_format, inverse_depth != 0, normalize_flow != 0);
   DEMON_LAUNCH_CHECK();
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(128) flow_to_depth_kernel(const T* __restrict_
                                                            const T* __restrict__ rotation, const T* __restrict__ translation,
                                                            T* __restrict__ depth, int H, int W, int rotation_format,
                                                            bool inverse_depth, bool normalized_flow) {
-  __shared__ F2DCamera<T> cam;
+  __shared__ F2DCamera cam;
   const int n = blockIdx.y;
   if (threadIdx.x == 0)
     f2d_camera(cam, intrinsics + 4 * n, rotation + (size_t)n * rotation_step(rotation_format), translation + 3 * n,
@@ -146,10 +146,10 @@ __global__ void __launch_bounds__(128) flow_to_depth_kernel(const T* __restrict_
 template <class T>
 static int flow_to_depth_launch(const T* flow, const T* intrinsics, const T* rotation, const T* translation, T* depth,
                                 int n, int h, int w, int rotation_format, int inverse_depth, int normalized_flow, void* stream) {
-  DEMON_REQUIRE(flow && intrinsics && rotation && translation && depth, "flow_to_depth: null pointer");
   DEMON_REQUIRE(rotation_format >= 0 && rotation_format <= 2, "flow_to_depth: rotation_format %d", rotation_format);
   DEMON_REQUIRE(n >= 0 && h >= 0 && w >= 0 && n <= 65535, "flow_to_depth: bad size");
   if ((int64_t)n * h * w == 0) return DEMON_OK;
+  DEMON_REQUIRE(flow && intrinsics && rotation && translation && depth, "flow_to_depth: null pointer");
   flow_to_depth_kernel<T><<<dim3(ceil_div(h * w, 128), n), 128, 0, (cudaStream_t)stream>>>(
       flow, intrinsics, rotation, translation, depth, h, w, rotation_format, inverse_depth != 0, normalized_flow != 0);
   DEMON_LAUNCH_CHECK();

@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(256) flow_extra_kernel(const float* __restrict
 __global__ void __launch_bounds__(128) dm_extra_kernel(const float* __restrict__ flowconf2, const float* __restrict__ motion_prev,
                                                       const float* __restrict__ image2_2, float* __restrict__ extra, int H, int W,
                                                       int extra_pitch, bool with_depth) {
-  __shared__ F2DCamera<float> cam;
+  __shared__ F2DCamera cam;
   const int n = blockIdx.y;
   if (with_depth && threadIdx.x == 0) {
     const float K[4] = {0.89115971f, 1.18821287f, 0.5f, 0.5f};
@@ -764,6 +764,8 @@ int demon_net_finalize(demon_net* n) {
   n->finalized = true;
   return DEMON_OK;
 }
+
+int demon_debug_tc_timeouts(void) { return tc_read_error_flag(); }
 
 int demon_net_batch(const demon_net* n) { return n ? n->B : 0; }
 int64_t demon_net_workspace_bytes(const demon_net* n) { return n ? (int64_t)(n->ws_floats * sizeof(float)) : 0; }

@@ -178,6 +178,9 @@ const char* demon_net_layer_name(const demon_net* net, int i);
 int demon_net_layer_profile(const demon_net* net, int i, double* ms, int64_t* calls, int* launches_per_call,
                             int* uses_tc);
 
+/* 1 if a pipeline wait inside the tcgen05 kernel ever timed out in this process (synchronises the device). */
+int demon_debug_tc_timeouts(void);
+
 /* Standalone convolution entry used by tests to compare the tcgen05 path with the fp32 SIMT path on
  * the same NHWC tensors.  in [B,H,W,Cin], kernel TF layout [kh,kw,cin,cout] (host), bias [cout] (host)
  * -> out [B,ceil(H/sy),ceil(W/sx),Cout]; caffe padding (helpers.py:70-94). */

@@ -162,9 +162,13 @@ def test_reference_round_trip_on_gpu(ops, dtype, inverse_depth, normalize_flow):
 
 @pytest.mark.parametrize("dtype", TYPES)
 def test_flow_to_depth_matches_oracle(ops, dtype):
-    """The reference solves each pixel with a float JacobiSVD, the kernel with QR in double: both are
-    backward stable, so they agree to cond(A) * eps(T) -- the reference test's own tolerance 1e-4 holds
-    against the T oracle, and 1e-6 against the double oracle."""
+    """The triangulation is ill conditioned on some pixels (cond(A) up to 1e5 for arbitrary flows): the
+    reference's float JacobiSVD carries cond * 6e-8 of noise there, and so does the float oracle (its own
+    realisation of it -- the double oracle differs from the float oracle by up to 1e-3 on those pixels).  The
+    kernel carries double from the float inputs to the solved point, so:
+      * against the DOUBLE oracle (same float inputs) it must agree to float output rounding everywhere;
+      * against the FLOAT oracle it must agree within the reference test's own 1e-4 (test_FlowToDepth2.py:70)
+        except on the ill-conditioned pixels, where it must be no further than the float oracle's own noise."""
     rng = np.random.RandomState(9)
     n = 2
     flow = rng.uniform(-0.08, 0.08, (n, 2, 48, 64)).astype(dtype)
@@ -178,14 +182,15 @@ def test_flow_to_depth_matches_oracle(ops, dtype):
     ref_d = oops.flow_to_depth2(flow.astype(np.float64), K.astype(np.float64), r.astype(np.float64), t.astype(np.float64),
                                 normalized_flow=True, inverse_depth=True)
     assert g.shape == (n, 1, 48, 64) and g[0, 0, 0, 0] == 0
-    # zero / non-zero pattern (behind camera -> 0) may differ only where the triangulated depth is ~infinite
-    both = (g != 0) & (ref_t != 0)
-    assert ((g != 0) != (ref_t != 0)).mean() < 2e-3
-    np.testing.assert_allclose(g[both], ref_t[both], rtol=1e-4, atol=1e-4)
-    tight = 1e-5 if dtype == np.float32 else 1e-9
-    both_d = (g != 0) & (ref_d != 0)
-    err = np.abs(g[both_d] - ref_d[both_d]) / np.maximum(np.abs(ref_d[both_d]), 1e-3)
-    assert np.median(err) < tight, np.median(err)
+    assert ((g != 0) != (ref_d != 0)).mean() < 1e-3          # behind-camera pattern (only ~infinite depths may flip)
+    both = (g != 0) & (ref_d != 0)
+    err_d = np.abs(g[both] - ref_d[both]) / np.abs(ref_d[both])
+    assert err_d.max() < (4e-7 if dtype == np.float32 else 1e-11), err_d.max()
+    both_t = (g != 0) & (ref_t != 0) & (ref_d != 0)
+    err_t = np.abs(g[both_t] - ref_t[both_t]) / np.abs(ref_t[both_t])
+    noise = np.abs(ref_t[both_t] - ref_d[both_t]) / np.abs(ref_d[both_t])       # the float oracle's own noise
+    assert (err_t > 1e-4).mean() < 0.01
+    assert (err_t <= 1e-4 + 1.01 * noise).all()
 
 
 def test_shapes_and_errors_on_gpu(ops):
