@@ -162,9 +162,16 @@ def synthetic_weights(seed=0, dtype=np.float32):
     (helpers.py:66-67 `variance_scaling_initializer()` defaults).  Biases are
     small and NON-zero so the bias path is exercised.  The three prediction
     heads are re-scaled so that the geometry ops between the blocks see
-    plausible values: inverse depth around 0.5 (mostly positive), rotation of
-    a few hundredths of a radian, translation near (0.9, 0.1, -0.05), scale
-    near 1, flow of a few percent of the image size.
+    a geometrically SELF-CONSISTENT regime, like a trained DeMoN does: inverse
+    depth around 0.5, rotation of a few hundredths of a radian, translation near
+    (0.9, 0.1, -0.05), scale near 1, and a flow prediction scattered around the
+    flow that this depth and motion imply, depth_to_flow(0.5, r, t) ~ (0.381,
+    0.035) of the image size.  Self-consistency matters for testing: where the
+    predicted flow contradicts the predicted motion the triangulation of
+    flow_to_depth (blocks_original.py:344) is singular (depth -> 1/0) and the
+    reference network itself amplifies one float ulp of its own flow
+    prediction into percent-level changes of its output -- no two float
+    implementations, the reference's CPU and GPU paths included, agree there.
     """
     rng = np.random.RandomState(seed)
     out = OrderedDict()
@@ -185,8 +192,8 @@ def synthetic_weights(seed=0, dtype=np.float32):
         out[prefix + "/bias"] = np.asarray(bias, dtype=dtype)
 
     for scope in ("netFlow1", "netFlow2"):
-        rescale(scope + "/predict_flow5/conv2", 0.05, [0.01, -0.01, 0.3, 0.3])
-        rescale(scope + "/predict_flow2/conv2", 0.05, [0.015, -0.01, 0.3, 0.3])
+        rescale(scope + "/predict_flow5/conv2", 0.02, [0.381, 0.035, 0.3, 0.3])
+        rescale(scope + "/predict_flow2/conv2", 0.02, [0.381, 0.035, 0.3, 0.3])
     for scope in ("netDM1", "netDM2"):
         rescale(scope + "/predict_depthnormal2/conv2", 0.1, [0.5, 0.0, 0.0, -0.8])
         rescale(scope + "/motion_fc3", 0.05, [0.02, -0.03, 0.01, 0.9, 0.1, -0.05, 1.0])

@@ -230,15 +230,20 @@ def test_batch_consistency_and_determinism_at_benchmark_batch(sessions, syntheti
 
 
 def test_adversarial_weights_exercise_invalid_geometry_branches(synthetic_weights):
-    """Negative / zero inverse depths and a large motion: depth_to_flow yields NaN, the |flow| < 1 gate
-    (blocks_original.py:165-168) zeroes it, flow_to_depth returns 0 behind the camera.  Outputs must stay
-    finite and match the oracle."""
-    from demon_b200.networks_original import Session, DemonPipeline
+    """Weights that make the previous depth straddle zero and the motion large: depth_to_flow yields NaN, the
+    |flow| < 1 gate (blocks_original.py:165-168) zeroes it, warp2d leaves the image, flow_to_depth triangulates
+    behind the camera (-> 0) or near the singularity.  netFlow2's output only passes through the EXACT ops
+    (depth_to_flow, gate, warp2d), so it must still match tightly.  netDM2's passes through the singular
+    triangulation, where the reference function itself amplifies float rounding of its own flow to percent level
+    (see demon_b200/weights.py: synthetic_weights) -- there only finiteness and a loose bound are asserted."""
+    from demon_b200.networks_original import Session, IterativeNet
     w = dict(synthetic_weights)
     for scope in ("netDM1", "netDM2"):
         w[scope + "/predict_depthnormal2/conv2/bias"] = np.array([0.0, 0, 0, -0.8], np.float32)      # depth straddles 0
         w[scope + "/predict_depthnormal2/conv2/kernel"] = synthetic_weights[scope + "/predict_depthnormal2/conv2/kernel"] * 5
         w[scope + "/motion_fc3/bias"] = np.array([0.3, -0.2, 0.1, 2.5, 0.5, -0.7, 1.0], np.float32)  # large motion
+    for scope in ("netFlow1", "netFlow2"):
+        w[scope + "/predict_flow2/conv2/bias"] = np.array([0.01, -0.01, 0.3, 0.3], np.float32)       # flow contradicts the motion
     s = Session("3xtf32")
     s.load_weights(w)
     g = torch.Generator().manual_seed(99)
@@ -247,15 +252,15 @@ def test_adversarial_weights_exercise_invalid_geometry_branches(synthetic_weight
     orc = OracleNets(w)
     r0 = orc.bootstrap(ip, i22)
     assert (r0["predict_depth2"].numpy() <= 0).mean() > 0.05
-    ref_it = orc.iterative(ip, i22, r0["predict_depth2"], r0["predict_normal2"], r0["predict_rotation"], r0["predict_translation"], full=True)
-    assert (ref_it["flow_from_depth_motion"].numpy() == 0).mean() > 0.05       # gated pixels
-    out = DemonPipeline(s, 1, 3).forward(torch.from_numpy(ip).cuda(), torch.from_numpy(i22).cuda())
-    torch.cuda.synchronize()
-    ref = orc.pipeline(ip, i22)
-    d = out["predict_depth0"].cpu().numpy()
-    assert np.isfinite(d).all()
-    assert l1_rel(d, ref["predict_depth0"].numpy()) < 10 * TOL     # threshold flips of single pixels are allowed to show
-    assert epe(out["predict_flow2"].cpu().numpy(), ref["predict_flow2"].numpy()) < 10 * TOL
+    args = (ip, i22, r0["predict_depth2"].numpy(), r0["predict_normal2"].numpy(), r0["predict_rotation"].numpy(),
+            r0["predict_translation"].numpy())
+    ref = orc.iterative(*args, full=True)
+    assert (ref["flow_from_depth_motion"].numpy() == 0).mean() > 0.05       # NaN / gated pixels
+    out = IterativeNet(s, "channels_first", 1).eval(*args)
+    assert all(np.isfinite(v).all() for v in out.values())
+    assert epe(out["predict_flow2"], ref["predict_flow2"].numpy()) < TOL
+    assert epe(out["predict_flow5"], ref["predict_flow5"].numpy()) < TOL
+    assert l1_rel(out["predict_depth2"], ref["predict_depth2"].numpy()) < 0.2
 
 
 def test_refinement_at_1024x768(sessions, synthetic_weights):
