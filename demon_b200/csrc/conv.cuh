@@ -43,6 +43,10 @@ struct ConvProblem {
   int leaky;          // apply max(0.1f*x, x)
   const float* scale; // optional [B]: channel 0 is multiplied by scale[n*scale_stride] after bias (depth = scale * ch0,
   int scale_stride;   //   blocks_original.py:281-283)
+  // split-K (dense layers, SIMT path only): `ksplit` CTAs along K write partial sums to `partial`
+  // ([ksplit][M][Cout_pad] floats) and a second kernel reduces them in a fixed order (deterministic)
+  float* partial;
+  int ksplit;
 };
 
 // fp32 CUDA-core implicit GEMM (conv_simt.cu)

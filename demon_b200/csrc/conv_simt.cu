@@ -47,28 +47,37 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvProblem p) {
   const int bk = tid / TXN;            // 0..15 when active
   const int bn = (tid % TXN) * 4;
 
-  const int nchunks = (p.Cin + BK - 1) / BK;
-  const int nk = p.ntaps * nchunks;
+  // The GEMM K axis is the flattened (tap, channel) index: k = tap * Cin + ci.  Cin is a multiple of 4, so every
+  // float4 of a K chunk lies inside one tap -- layers with 4, 8 or 12 input channels fill their 16-wide chunks with
+  // several taps instead of padding.  blockIdx.z selects a contiguous range of K chunks (split-K, dense layers).
+  const int Ktot = p.ntaps * p.Cin;
+  const int nk_all = (Ktot + BK - 1) / BK;
+  const int per_split = (nk_all + gridDim.z - 1) / gridDim.z;
+  const int it_begin = blockIdx.z * per_split;
+  const int it_end = min(nk_all, it_begin + per_split);
+  const int nk = max(0, it_end - it_begin);
 
   float4 a_reg[ROWS_PER_THREAD_LD];
   float4 b_reg;
 
   auto load_global = [&](int it) {
-    const int tap = it / nchunks;
-    const int c0 = (it - tap * nchunks) * BK;
-    const int dy = p.dy[tap], dx = p.dx[tap];
-    const int ci = c0 + kv * 4;
+    const int k0 = (it_begin + it) * BK;
+    const int ka = k0 + kv * 4;
+    const int tap = ka / p.Cin;
+    const int ci = ka - tap * p.Cin;
+    const bool kvalid = ka < Ktot;
+    const int dy = kvalid ? p.dy[tap] : 0, dx = kvalid ? p.dx[tap] : 0;
 #pragma unroll
     for (int i = 0; i < ROWS_PER_THREAD_LD; ++i) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       const int iy = row_y[i] + dy, ix = row_x[i] + dx;
-      if (row_n[i] >= 0 && ci < p.Cin && iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi)
+      if (row_n[i] >= 0 && kvalid && iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi)
         v = __ldg(reinterpret_cast<const float4*>(p.in + ((size_t)(row_n[i] * p.Hi + iy) * p.Wi + ix) * p.in_pitch + ci));
       a_reg[i] = v;
     }
     b_reg = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (b_active && c0 + bk < p.Cin && n0 + bn < p.Cout_pad)
-      b_reg = __ldg(reinterpret_cast<const float4*>(p.w + ((size_t)tap * p.Cin + c0 + bk) * p.Cout_pad + n0 + bn));
+    if (b_active && k0 + bk < Ktot && n0 + bn < p.Cout_pad)
+      b_reg = __ldg(reinterpret_cast<const float4*>(p.w + (size_t)(k0 + bk) * p.Cout_pad + n0 + bn));
   };
   auto store_smem = [&]() {
 #pragma unroll
@@ -89,8 +98,10 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvProblem p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  load_global(0);
-  store_smem();
+  if (nk > 0) {
+    load_global(0);
+    store_smem();
+  }
   __syncthreads();
   for (int it = 0; it < nk; ++it) {
     if (it + 1 < nk) load_global(it + 1);
@@ -115,6 +126,15 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvProblem p) {
   // ---- epilogue: bias, leaky ReLU, per-sample scale on channel 0, write into the concat slice ----
   const int col = n0 + tx * 4;
   if (col >= p.Cout) return;
+  if (p.partial != nullptr) {   // split-K: raw partial sums [z][M][Cout_pad], reduced by splitk_reduce_kernel
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + ty * 4 + i;
+      if (m < M && col < p.Cout_pad)
+        *reinterpret_cast<float4*>(p.partial + ((size_t)blockIdx.z * M + m) * p.Cout_pad + col) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+    return;
+  }
   float bias[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) bias[j] = (col + j < p.Cout_pad) ? __ldg(p.bias + col + j) : 0.f;
@@ -145,6 +165,19 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvProblem p) {
   }
 }
 
+// out[m][c] = act(bias[c] + sum_z partial[z][m][c]); only used for 1x1 problems on 1x1 images (dense layers)
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const ConvProblem p, int ksplit, int M) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= M * p.Cout) return;
+  const int m = i / p.Cout, c = i - m * p.Cout;
+  float s = 0.f;
+  for (int z = 0; z < ksplit; ++z) s += p.partial[((size_t)z * M + m) * p.Cout_pad + c];
+  s += __ldg(p.bias + c);
+  if (p.leaky) s = fmaxf(0.1f * s, s);
+  if (p.scale != nullptr && c == 0) s *= __ldg(p.scale + (size_t)m * p.scale_stride);
+  p.out[(size_t)m * p.out_pitch + c] = s;
+}
+
 }  // namespace
 
 int conv_simt_launch(const ConvProblem& p, cudaStream_t stream) {
@@ -155,21 +188,29 @@ int conv_simt_launch(const ConvProblem& p, cudaStream_t stream) {
   const int64_t M = (int64_t)p.B * p.Ho * p.Wo;
   DEMON_REQUIRE(M < (1ll << 31), "conv: too many output pixels");
   if (M == 0 || p.Cout == 0) return DEMON_OK;
+  const int ks = (p.partial != nullptr && p.ksplit > 1) ? p.ksplit : 1;
+  if (ks > 1) DEMON_REQUIRE(p.Hi == 1 && p.Wi == 1 && p.Ho == 1 && p.Wo == 1, "conv: split-K is for dense layers only");
+  ConvProblem q = p;
+  if (ks == 1) q.partial = nullptr;
   // tile choice: widest N tile that the layer fills
   if (p.Cout > 32) {
-    dim3 grid(ceil_div((int)M, 64), ceil_div(p.Cout, 64));
-    conv_simt_kernel<64, 64><<<grid, 256, 0, stream>>>(p);
+    dim3 grid(ceil_div((int)M, 64), ceil_div(p.Cout, 64), ks);
+    conv_simt_kernel<64, 64><<<grid, 256, 0, stream>>>(q);
   } else if (p.Cout > 16) {
-    dim3 grid(ceil_div((int)M, 128), ceil_div(p.Cout, 32));
-    conv_simt_kernel<128, 32><<<grid, 256, 0, stream>>>(p);
+    dim3 grid(ceil_div((int)M, 128), ceil_div(p.Cout, 32), ks);
+    conv_simt_kernel<128, 32><<<grid, 256, 0, stream>>>(q);
   } else if (p.Cout > 8) {
-    dim3 grid(ceil_div((int)M, 256), ceil_div(p.Cout, 16));
-    conv_simt_kernel<256, 16><<<grid, 256, 0, stream>>>(p);
+    dim3 grid(ceil_div((int)M, 256), ceil_div(p.Cout, 16), ks);
+    conv_simt_kernel<256, 16><<<grid, 256, 0, stream>>>(q);
   } else {
-    dim3 grid(ceil_div((int)M, 512), ceil_div(p.Cout, 8));
-    conv_simt_kernel<512, 8><<<grid, 256, 0, stream>>>(p);
+    dim3 grid(ceil_div((int)M, 512), ceil_div(p.Cout, 8), ks);
+    conv_simt_kernel<512, 8><<<grid, 256, 0, stream>>>(q);
   }
   DEMON_LAUNCH_CHECK();
+  if (ks > 1) {
+    splitk_reduce_kernel<<<ceil_div((int)M * p.Cout, 256), 256, 0, stream>>>(q, ks, (int)M);
+    DEMON_LAUNCH_CHECK();
+  }
   return DEMON_OK;
 }
 

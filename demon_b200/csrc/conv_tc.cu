@@ -36,6 +36,10 @@ struct TcParams {
   int tw, th, tb;
   int tiles_x, tiles_y, tiles_b, n_tiles, total_tiles;
   int ntaps, k_chunks;
+  // `nclass` independent problems share the input, the tiling and the launch (the four sub-pixel classes of a
+  // transposed convolution): class c uses taps [c*ntaps, (c+1)*ntaps), its own weight block and output offset.
+  int nclass;
+  int cls_ooy[4], cls_oox[4];
   int tap_c[kMaxTaps];   // coordinate offset in dim 0 (rx * in_pitch)
   int tap_qx[kMaxTaps];  // offset in dim 1 (W / sx)
   int tap_ry[kMaxTaps];  // coordinate in dim 2 (row parity)
@@ -49,7 +53,7 @@ struct TcParams {
   int stage_bytes;       // smem bytes of one pipeline stage
   // epilogue
   float* out;
-  int out_pitch, B, Ho, Wo, Hfull, Wfull, osy, osx, ooy, oox, Cout;
+  int out_pitch, B, Ho, Wo, Hfull, Wfull, osy, osx, Cout;
   const float* bias;
   int leaky;
   int* err;
@@ -171,9 +175,11 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-__device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& nt, int& n0, int& y0, int& x0) {
+__device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& cls, int& nt, int& n0, int& y0, int& x0) {
   nt = tile % p.n_tiles;
   int m = tile / p.n_tiles;
+  cls = m % p.nclass;
+  m /= p.nclass;
   const int xb = m % p.tiles_x;
   m /= p.tiles_x;
   const int yb = m % p.tiles_y;
@@ -224,11 +230,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       uint32_t phase = 0;
       const uint32_t tx = kATileBytes + (uint32_t)p.w_stage_bytes;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int nt, n0, y0, x0;
-        decode_tile(p, tile, nt, n0, y0, x0);
-        const unsigned char* wsrc = p.w + (size_t)nt * ksteps * p.w_stage_bytes;
+        int cls, nt, n0, y0, x0;
+        decode_tile(p, tile, cls, nt, n0, y0, x0);
+        const unsigned char* wsrc = p.w + (size_t)(cls * p.n_tiles + nt) * ksteps * p.w_stage_bytes;
         for (int ks = 0; ks < ksteps; ++ks) {
-          const int tap = ks / p.k_chunks, kc = ks - tap * p.k_chunks;
+          const int tap = cls * p.ntaps + ks / p.k_chunks, kc = ks % p.k_chunks;
           mbar_wait(empty0 + 8 * stage, phase ^ 1, p.err);
           const uint32_t sbase = smem_u32(smem + (size_t)stage * p.stage_bytes);
           mbar_expect_tx(full0 + 8 * stage, tx);
@@ -310,15 +316,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int xl = m % p.tw, yl = (m / p.tw) % p.th, nl = m / (p.tw * p.th);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      int nt, n0, y0, x0;
-      decode_tile(p, tile, nt, n0, y0, x0);
+      int cls, nt, n0, y0, x0;
+      decode_tile(p, tile, cls, nt, n0, y0, x0);
       const int a = it & 1;
       mbar_wait(afull0 + 8 * a, (it >> 1) & 1, p.err);
       __syncwarp();
       tc_fence_after();
       const int n = n0 + nl, oy = y0 + yl, ox = x0 + xl;
       const bool valid = n < p.B && oy < p.Ho && ox < p.Wo;
-      float* orow = p.out + ((size_t)(n * p.Hfull + oy * p.osy + p.ooy) * p.Wfull + ox * p.osx + p.oox) * p.out_pitch;
+      float* orow = p.out + ((size_t)(n * p.Hfull + oy * p.osy + p.cls_ooy[cls]) * p.Wfull + ox * p.osx + p.cls_oox[cls]) * p.out_pitch;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.n_tile);
       const int cbase = nt * p.n_tile;
       for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
@@ -433,41 +439,53 @@ bool tc_layer_supported(const ConvProblem& p) {
   return true;
 }
 
-int tc_layer_prepare(TcLayer& t, const ConvProblem& p, const float* w_host, int precision) {
-  DEMON_REQUIRE(tc_layer_supported(p), "tc_layer_prepare: unsupported shape");
+int tc_layer_prepare(TcLayer& t, const ConvProblem* probs, const float* const* w_hosts, int nclass, int precision) {
+  DEMON_REQUIRE(nclass >= 1 && nclass <= 4, "tc_layer_prepare: nclass %d", nclass);
+  const ConvProblem& p = probs[0];
+  for (int c = 0; c < nclass; ++c) {
+    DEMON_REQUIRE(tc_layer_supported(probs[c]), "tc_layer_prepare: unsupported shape");
+    DEMON_REQUIRE(probs[c].ntaps == p.ntaps && probs[c].in == p.in && probs[c].Cout == p.Cout, "tc_layer_prepare: classes must share the input");
+  }
+  DEMON_REQUIRE(nclass * p.ntaps <= kMaxTaps, "tc_layer_prepare: too many taps");
+  t.nclass = nclass;
   t.nsplit = (precision == DEMON_PREC_TF32) ? 1 : 3;
-  const int cout16 = (p.Cout + 15) / 16 * 16;
-  t.n_tile = cout16 <= 256 ? cout16 : 256;
-  t.n_tiles = ceil_div(p.Cout, t.n_tile);
-  t.k_chunks = p.Cin / 32;
   const Tiling tl = choose_tiling(p.B, p.Ho, p.Wo);
   t.tw = tl.tw; t.th = tl.th; t.tb = tl.tb;
+  const int m_tiles = tl.tiles_x * tl.tiles_y * tl.tiles_b * nclass;
+  // N tile: as wide as one UMMA allows, narrowed (down to 64) while the layer would leave SMs idle
+  const int cout16 = (p.Cout + 15) / 16 * 16;
+  int n_tile = cout16 <= 256 ? cout16 : 256;
+  while (n_tile >= 128 && (n_tile % 32) == 0 && m_tiles * ceil_div(p.Cout, n_tile) < num_sms()) n_tile /= 2;
+  t.n_tile = n_tile;
+  t.n_tiles = ceil_div(p.Cout, t.n_tile);
+  t.k_chunks = p.Cin / 32;
   const int w_block = t.n_tile * 128 * (t.nsplit == 3 ? 2 : 1);
   const int stage_bytes = 2 * kATileBytes + 2 * t.n_tile * 128;
   t.stages = std::min(8, (220 * 1024) / stage_bytes);
   DEMON_REQUIRE(t.stages >= 2, "tc_layer_prepare: not enough shared memory for two stages");
   t.smem_bytes = t.stages * stage_bytes + 1024;
 
-  // ---- weights: per (n-tile, tap, chunk): [W_hi | W_lo], each n_tile rows of 32 fp32, K-major, pre-swizzled (SW128) ----
-  const size_t total = (size_t)t.n_tiles * p.ntaps * t.k_chunks * w_block;
+  // ---- weights: per (class, n-tile, tap, chunk): [W_hi | W_lo], each n_tile rows of 32 fp32, K-major, pre-swizzled ----
+  const size_t total = (size_t)nclass * t.n_tiles * p.ntaps * t.k_chunks * w_block;
   std::vector<unsigned char> packed(total, 0);
-  for (int nt = 0; nt < t.n_tiles; ++nt)
-    for (int tap = 0; tap < p.ntaps; ++tap)
-      for (int kc = 0; kc < t.k_chunks; ++kc) {
-        unsigned char* blk = packed.data() + ((size_t)(nt * p.ntaps + tap) * t.k_chunks + kc) * w_block;
-        for (int r = 0; r < t.n_tile; ++r) {
-          const int co = nt * t.n_tile + r;
-          for (int k = 0; k < 32; ++k) {
-            float w = 0.f;
-            if (co < p.Cout) w = w_host[((size_t)tap * p.Cin + kc * 32 + k) * p.Cout_pad + co];
-            const float hi = (t.nsplit == 3) ? tf32_round(w) : w;
-            const float lo = w - hi;
-            const size_t off = (size_t)r * 128 + (size_t)(((k >> 2) ^ (r & 7)) << 4) + (size_t)(k & 3) * 4;
-            memcpy(blk + off, &hi, 4);
-            if (t.nsplit == 3) memcpy(blk + (size_t)t.n_tile * 128 + off, &lo, 4);
+  for (int cls = 0; cls < nclass; ++cls)
+    for (int nt = 0; nt < t.n_tiles; ++nt)
+      for (int tap = 0; tap < p.ntaps; ++tap)
+        for (int kc = 0; kc < t.k_chunks; ++kc) {
+          unsigned char* blk = packed.data() + ((size_t)((cls * t.n_tiles + nt) * p.ntaps + tap) * t.k_chunks + kc) * w_block;
+          for (int r = 0; r < t.n_tile; ++r) {
+            const int co = nt * t.n_tile + r;
+            for (int k = 0; k < 32; ++k) {
+              float w = 0.f;
+              if (co < p.Cout) w = w_hosts[cls][((size_t)tap * p.Cin + kc * 32 + k) * p.Cout_pad + co];
+              const float hi = (t.nsplit == 3) ? tf32_round(w) : w;
+              const float lo = w - hi;
+              const size_t off = (size_t)r * 128 + (size_t)(((k >> 2) ^ (r & 7)) << 4) + (size_t)(k & 3) * 4;
+              memcpy(blk + off, &hi, 4);
+              if (t.nsplit == 3) memcpy(blk + (size_t)t.n_tile * 128 + off, &lo, 4);
+            }
           }
         }
-      }
   void* dw = nullptr;
   DEMON_CHECK_CUDA(cudaMalloc(&dw, total));
   DEMON_CHECK_CUDA(cudaMemcpy(dw, packed.data(), total, cudaMemcpyHostToDevice));
@@ -509,19 +527,26 @@ int* tc_error_flag() {
   return flag;
 }
 
-int conv_tc_launch(const TcLayer& t, const ConvProblem& p, cudaStream_t stream) {
+int conv_tc_launch(const TcLayer& t, const ConvProblem* probs, cudaStream_t stream) {
+  const ConvProblem& p = probs[0];
   TcParams prm;
   memset(&prm, 0, sizeof(prm));
   const Tiling tl = choose_tiling(p.B, p.Ho, p.Wo);
   prm.tw = t.tw; prm.th = t.th; prm.tb = t.tb;
   prm.tiles_x = tl.tiles_x; prm.tiles_y = tl.tiles_y; prm.tiles_b = tl.tiles_b;
   prm.n_tiles = t.n_tiles;
-  prm.total_tiles = tl.tiles_x * tl.tiles_y * tl.tiles_b * t.n_tiles;
+  prm.nclass = t.nclass;
+  prm.total_tiles = tl.tiles_x * tl.tiles_y * tl.tiles_b * t.n_tiles * t.nclass;
   prm.ntaps = p.ntaps; prm.k_chunks = t.k_chunks;
-  for (int i = 0; i < p.ntaps; ++i) {
-    const int qy = floor_div(p.dy[i], p.sy), qx = floor_div(p.dx[i], p.sx);
-    prm.tap_qy[i] = qy; prm.tap_ry[i] = p.dy[i] - qy * p.sy;
-    prm.tap_qx[i] = qx; prm.tap_c[i] = (p.dx[i] - qx * p.sx) * p.in_pitch;
+  for (int c = 0; c < t.nclass; ++c) {
+    const ConvProblem& q = probs[c];
+    prm.cls_ooy[c] = q.ooy; prm.cls_oox[c] = q.oox;
+    for (int i = 0; i < q.ntaps; ++i) {
+      const int qy = floor_div(q.dy[i], q.sy), qx = floor_div(q.dx[i], q.sx);
+      const int e = c * q.ntaps + i;
+      prm.tap_qy[e] = qy; prm.tap_ry[e] = q.dy[i] - qy * q.sy;
+      prm.tap_qx[e] = qx; prm.tap_c[e] = (q.dx[i] - qx * q.sx) * q.in_pitch;
+    }
   }
   prm.w = static_cast<const unsigned char*>(t.w_packed);
   prm.n_tile = t.n_tile; prm.nsplit = t.nsplit;
@@ -529,7 +554,7 @@ int conv_tc_launch(const TcLayer& t, const ConvProblem& p, cudaStream_t stream) 
   prm.stages = t.stages;
   prm.stage_bytes = 2 * kATileBytes + 2 * t.n_tile * 128;
   prm.out = p.out; prm.out_pitch = p.out_pitch; prm.B = p.B; prm.Ho = p.Ho; prm.Wo = p.Wo; prm.Hfull = p.Hfull; prm.Wfull = p.Wfull;
-  prm.osy = p.osy; prm.osx = p.osx; prm.ooy = p.ooy; prm.oox = p.oox; prm.Cout = p.Cout;
+  prm.osy = p.osy; prm.osx = p.osx; prm.Cout = p.Cout;
   prm.bias = p.bias; prm.leaky = p.leaky;
   prm.err = tc_error_flag();
   static bool attr_set = false;

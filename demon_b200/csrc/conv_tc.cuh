@@ -9,6 +9,7 @@ namespace demon {
 struct TcLayer {
   void* w_packed = nullptr;   // device, owned
   void* tmap_in = nullptr;    // device copy of the CUtensorMap (128 B), owned
+  int nclass = 1;             // 4 for the sub-pixel classes of a transposed convolution (one launch)
   int n_tile = 0;             // UMMA N of this layer (Cout rounded up to 16)
   int n_tiles = 0;            // grid.y
   int k_chunks = 0;           // Cin / 32
@@ -20,10 +21,12 @@ struct TcLayer {
 };
 
 bool tc_layer_supported(const ConvProblem& p);
-// w_host: [ntaps][Cin][Cout_pad] fp32, the same packing the SIMT path uses
-int tc_layer_prepare(TcLayer& t, const ConvProblem& p, const float* w_host, int precision);
+// `nclass` problems that share input, tiling and Cout (1 for a convolution, 4 for the sub-pixel classes of a transposed
+// convolution) are packed into one layer and run in ONE launch.  w_hosts[c]: [ntaps][Cin][Cout_pad] fp32, the same
+// packing the SIMT path uses.
+int tc_layer_prepare(TcLayer& t, const ConvProblem* probs, const float* const* w_hosts, int nclass, int precision);
 void tc_layer_free(TcLayer& t);
-int conv_tc_launch(const TcLayer& t, const ConvProblem& p, cudaStream_t stream);
+int conv_tc_launch(const TcLayer& t, const ConvProblem* probs, cudaStream_t stream);
 // 1 if any mbarrier wait of the tcgen05 kernel has timed out since process start (pipeline bug detector)
 int tc_read_error_flag();
 

@@ -56,7 +56,9 @@ struct Layer {
   float* bias_dev = nullptr;
   // tensor-core path
   bool use_tc = false;
-  TcLayer tc[4];
+  TcLayer tc;
+  // split-K for dense layers (SIMT path)
+  int ksplit = 1;
 };
 
 struct HostVar {
@@ -93,7 +95,7 @@ struct demon_net {
   // named buffers
   Buf *img8, *i22, *i22_half, *c1y, *c1, *c2y, *cat2, *extra_in, *exy, *c21y, *concat2, *c3y, *c3, *c31y, *concat3, *c4y, *c4,
       *c41y, *concat4, *c5y, *c5, *c51y, *c51, *pf5a, *pf5, *p2a, *flowconf2, *dn2, *mc1, *fc1, *fc2, *motion;
-  Buf *rin, *concat0, *rc1, *concat1, *rc2, *rc21, *pd0a, *rdepth0;
+  Buf *rin, *concat0, *rc1, *concat1, *rc2, *rc21, *pd0a, *rdepth0, *splitk;
 
   Buf* add_buf(int H, int W, int C) {
     bufs.emplace_back(new Buf());
@@ -157,7 +159,8 @@ void build_flow_block(demon_net* n, const std::string& scope, bool iterative) {
   // _upsample_prediction: no activation (blocks_original.py:70); lands in concat4[512:514]
   n->add_layer(s + "upsample_flow5to4/upconv", L_DECONV, n->pf5, 0, 4, n->concat4, 512, 2, 4, 4, 2, 2, false);
   n->add_layer(s + "refine4/upconv", L_DECONV, n->c51, 0, 512, n->concat4, 0, 256, 4, 4, 2, 2, true);
-  n->add_layer(s + "refine3/upconv", L_DECONV, n->concat4, 0, 514, n->concat3, 0, 128, 4, 4, 2, 2, true);
+  Layer* r3 = n->add_layer(s + "refine3/upconv", L_DECONV, n->concat4, 0, 514, n->concat3, 0, 128, 4, 4, 2, 2, true);
+  r3->cin_buf = 544;   // channels 514..543 of concat4 are never written (zero) and carry zero weights
   n->add_layer(s + "refine2/upconv", L_DECONV, n->concat3, 0, 256, n->concat2, 0, 64, 4, 4, 2, 2, true);
   n->add_layer(s + "predict_flow2/conv1", L_CONV, n->concat2, 0, 128, n->p2a, 0, 24, 3, 3, 1, 1, true);
   n->add_layer(s + "predict_flow2/conv2", L_CONV, n->p2a, 0, 24, n->flowconf2, 0, 4, 3, 3, 1, 1, false);
@@ -169,7 +172,9 @@ void build_dm_block(demon_net* n, const std::string& scope, bool iterative) {
   n->add_layer(s + "motion_conv1", L_CONV, n->c51, 0, 512, n->mc1, 0, 128, 3, 3, 1, 1, true);
   Layer* f1 = n->add_layer(s + "motion_fc1", L_DENSE, n->mc1, 0, 6144, n->fc1, 0, 1024, 1, 1, 1, 1, true);
   f1->dense_nchw_flatten = true; f1->dense_c = 128; f1->dense_hw = 48;
-  n->add_layer(s + "motion_fc2", L_DENSE, n->fc1, 0, 1024, n->fc2, 0, 128, 1, 1, 1, 1, true);
+  f1->ksplit = 24;   // 16 column tiles x 24 K slices = 384 CTAs instead of 16
+  Layer* f2 = n->add_layer(s + "motion_fc2", L_DENSE, n->fc1, 0, 1024, n->fc2, 0, 128, 1, 1, 1, 1, true);
+  f2->ksplit = 16;
   n->add_layer(s + "motion_fc3", L_DENSE, n->fc2, 0, 128, n->motion, 0, 7, 1, 1, 1, 1, false);
   n->add_layer(s + "refine4/upconv", L_DECONV, n->c51, 0, 512, n->concat4, 0, 256, 4, 4, 2, 2, true);
   n->add_layer(s + "refine3/upconv", L_DECONV, n->concat4, 0, 512, n->concat3, 0, 128, 4, 4, 2, 2, true);
@@ -213,7 +218,7 @@ void build_plan(demon_net* n) {
   n->c4y = n->add_buf(12, 32, 256);
   n->c4 = n->add_buf(12, 16, 256);
   n->c41y = n->add_buf(12, 16, 256);
-  n->concat4 = n->add_buf(12, 16, 516);
+  n->concat4 = n->add_buf(12, 16, 544);   // 512 + 2 (upsampled flow) padded to a multiple of 32 for the tcgen05 path
   n->c5y = n->add_buf(6, 16, 512);
   n->c5 = n->add_buf(6, 8, 512);
   n->c51y = n->add_buf(6, 8, 512);
@@ -227,6 +232,7 @@ void build_plan(demon_net* n) {
   n->fc1 = n->add_buf(1, 1, 1024);
   n->fc2 = n->add_buf(1, 1, 128);
   n->motion = n->add_buf(1, 1, 8);
+  n->splitk = n->add_buf(1, 24, 1024);   // split-K partial sums [24][B][1024]
   const int RH = n->RH, RW = n->RW;
   n->rin = n->add_buf(RH, RW, 4);
   n->concat0 = n->add_buf(RH, RW, 64);
@@ -315,7 +321,8 @@ void fill_problem(const Layer& l, int B, ConvProblem& p) {
   p.osy = p.osx = 1;
 }
 
-int run_layer(const Layer& l, int B, cudaStream_t stream) {
+// The convolution problem(s) of a layer: 1 for conv / dense, 4 sub-pixel classes for a transposed conv.
+int build_problems(const Layer& l, int B, ConvProblem* out) {
   ConvProblem p;
   fill_problem(l, B, p);
   if (l.kind == L_DENSE) {
@@ -325,7 +332,8 @@ int run_layer(const Layer& l, int B, cudaStream_t stream) {
     p.sy = p.sx = 1;
     p.ntaps = 1;
     p.w = l.w_dev[0];
-    return conv_simt_launch(p, stream);
+    out[0] = p;
+    return 1;
   }
   p.Hi = l.in->H; p.Wi = l.in->W;
   if (l.kind == L_CONV) {
@@ -336,8 +344,8 @@ int run_layer(const Layer& l, int B, cudaStream_t stream) {
     for (int ky = 0; ky < l.kh; ++ky)
       for (int kx = 0; kx < l.kw; ++kx) { p.dy[ky * l.kw + kx] = ky - l.kh / 2; p.dx[ky * l.kw + kx] = kx - l.kw / 2; }
     p.w = l.w_dev[0];
-    if (l.use_tc) return conv_tc_launch(l.tc[0], p, stream);
-    return conv_simt_launch(p, stream);
+    out[0] = p;
+    return 1;
   }
   // transposed conv: four sub-pixel 2x2 convolutions
   p.sy = p.sx = 1;
@@ -351,22 +359,33 @@ int run_layer(const Layer& l, int B, cudaStream_t stream) {
       for (int a = 0; a < 2; ++a)
         for (int b = 0; b < 2; ++b) { p.dy[a * 2 + b] = kDeconvD[py][a]; p.dx[a * 2 + b] = kDeconvD[px][b]; }
       p.w = l.w_dev[py * 2 + px];
-      int rc = l.use_tc ? conv_tc_launch(l.tc[py * 2 + px], p, stream) : conv_simt_launch(p, stream);
-      if (rc != DEMON_OK) return rc;
+      out[py * 2 + px] = p;
     }
+  return 4;
+}
+
+int run_layer(const Layer& l, int B, cudaStream_t stream, float* splitk_ws = nullptr) {
+  ConvProblem probs[4];
+  const int nclass = build_problems(l, B, probs);
+  if (l.use_tc) return conv_tc_launch(l.tc, probs, stream);
+  for (int c = 0; c < nclass; ++c) {
+    if (l.kind == L_DENSE && l.ksplit > 1 && splitk_ws) { probs[c].partial = splitk_ws; probs[c].ksplit = l.ksplit; }
+    int rc = conv_simt_launch(probs[c], stream);
+    if (rc != DEMON_OK) return rc;
+  }
   return DEMON_OK;
 }
 
 int run_layer_profiled(demon_net* n, int idx, cudaStream_t stream) {
   const Layer& l = *n->layers[idx];
-  if (!n->profiling) return run_layer(l, n->B, stream);
+  if (!n->profiling) return run_layer(l, n->B, stream, n->splitk->p);
   if (n->prof_used + 2 > n->prof_events.size()) {
     const size_t old = n->prof_events.size();
     n->prof_events.resize(old + 1024);
     for (size_t i = old; i < n->prof_events.size(); ++i) DEMON_CHECK_CUDA(cudaEventCreate(&n->prof_events[i]));
   }
   DEMON_CHECK_CUDA(cudaEventRecord(n->prof_events[n->prof_used], stream));
-  int rc = run_layer(l, n->B, stream);
+  int rc = run_layer(l, n->B, stream, n->splitk->p);
   DEMON_CHECK_CUDA(cudaEventRecord(n->prof_events[n->prof_used + 1], stream));
   n->prof_layer.push_back(idx);
   n->prof_used += 2;
@@ -649,8 +668,7 @@ void demon_net_destroy(demon_net* n) {
   if (!n) return;
   for (void* p : n->dev_allocs) cudaFree(p);
   for (cudaEvent_t e : n->prof_events) cudaEventDestroy(e);
-  for (auto& l : n->layers)
-    for (int i = 0; i < 4; ++i) tc_layer_free(l->tc[i]);
+  for (auto& l : n->layers) tc_layer_free(l->tc);
   cudaFree(n->ws);
   delete n;
 }
@@ -718,44 +736,18 @@ int demon_net_finalize(demon_net* n) {
     }
     // tensor-core eligibility and packing
     if (n->precision != DEMON_PREC_FP32_SIMT && l.kind != L_DENSE) {
-      const int nclass = l.kind == L_DECONV ? 4 : 1;
-      ConvProblem p;
+      ConvProblem probs[4];
+      const int nclass = build_problems(l, n->B, probs);
       bool all = true;
-      for (int c = 0; c < nclass && all; ++c) {
-        fill_problem(l, n->B, p);
-        p.Hi = l.in->H; p.Wi = l.in->W;
-        if (l.kind == L_CONV) {
-          p.sy = l.sy; p.sx = l.sx; p.Ho = ceil_div(p.Hi, l.sy); p.Wo = ceil_div(p.Wi, l.sx); p.Hfull = p.Ho; p.Wfull = p.Wo;
-          p.ntaps = l.kh * l.kw;
-          for (int ky = 0; ky < l.kh; ++ky)
-            for (int kx = 0; kx < l.kw; ++kx) { p.dy[ky * l.kw + kx] = ky - l.kh / 2; p.dx[ky * l.kw + kx] = kx - l.kw / 2; }
-        } else {
-          p.sy = p.sx = 1; p.Ho = p.Hi; p.Wo = p.Wi; p.Hfull = 2 * p.Hi; p.Wfull = 2 * p.Wi; p.osy = p.osx = 2; p.ntaps = 4;
-          p.ooy = c / 2; p.oox = c % 2;
-          for (int a = 0; a < 2; ++a)
-            for (int bb = 0; bb < 2; ++bb) { p.dy[a * 2 + bb] = kDeconvD[c / 2][a]; p.dx[a * 2 + bb] = kDeconvD[c % 2][bb]; }
-        }
-        all = tc_layer_supported(p);
-      }
+      for (int c = 0; c < nclass; ++c) all = all && tc_layer_supported(probs[c]);
       if (all) {
+        std::vector<float> cls_w[4];
+        const float* ptrs[4] = {nullptr, nullptr, nullptr, nullptr};
         for (int c = 0; c < nclass; ++c) {
-          // host copy of this class' weights in [tap][cin_buf][cout_pad]
-          if (l.kind == L_CONV) pack_conv(l, k, packed); else pack_deconv_class(l, k, c / 2, c % 2, packed);
-          fill_problem(l, n->B, p);
-          p.Hi = l.in->H; p.Wi = l.in->W;
-          if (l.kind == L_CONV) {
-            p.sy = l.sy; p.sx = l.sx; p.Ho = ceil_div(p.Hi, l.sy); p.Wo = ceil_div(p.Wi, l.sx); p.Hfull = p.Ho; p.Wfull = p.Wo;
-            p.ntaps = l.kh * l.kw;
-            for (int ky = 0; ky < l.kh; ++ky)
-              for (int kx = 0; kx < l.kw; ++kx) { p.dy[ky * l.kw + kx] = ky - l.kh / 2; p.dx[ky * l.kw + kx] = kx - l.kw / 2; }
-          } else {
-            p.sy = p.sx = 1; p.Ho = p.Hi; p.Wo = p.Wi; p.Hfull = 2 * p.Hi; p.Wfull = 2 * p.Wi; p.osy = p.osx = 2; p.ntaps = 4;
-            p.ooy = c / 2; p.oox = c % 2;
-            for (int a = 0; a < 2; ++a)
-              for (int bb = 0; bb < 2; ++bb) { p.dy[a * 2 + bb] = kDeconvD[c / 2][a]; p.dx[a * 2 + bb] = kDeconvD[c % 2][bb]; }
-          }
-          if ((rc = tc_layer_prepare(l.tc[c], p, packed.data(), n->precision))) return rc;
+          if (l.kind == L_CONV) pack_conv(l, k, cls_w[c]); else pack_deconv_class(l, k, c / 2, c % 2, cls_w[c]);
+          ptrs[c] = cls_w[c].data();
         }
+        if ((rc = tc_layer_prepare(l.tc, probs, ptrs, nclass, n->precision))) return rc;
         l.use_tc = true;
       }
     }
@@ -814,7 +806,7 @@ int demon_net_layer_profile(const demon_net* n, int i, double* ms, int64_t* call
   DEMON_REQUIRE(n && i >= 0 && i < (int)n->layers.size(), "layer index");
   if (ms) *ms = i < (int)n->prof_ms.size() ? n->prof_ms[i] : 0.0;
   if (calls) *calls = i < (int)n->prof_calls.size() ? n->prof_calls[i] : 0;
-  if (launches_per_call) *launches_per_call = n->layers[i]->kind == L_DECONV ? 4 : 1;
+  if (launches_per_call) *launches_per_call = n->layers[i]->use_tc ? 1 : (n->layers[i]->kind == L_DECONV ? 4 : (n->layers[i]->ksplit > 1 ? 2 : 1));
   if (uses_tc) *uses_tc = n->layers[i]->use_tc ? 1 : 0;
   return DEMON_OK;
 }
@@ -953,34 +945,29 @@ static int standalone_conv(const float* in, float* out, int B, int H, int W, int
   int rc;
   if ((rc = upload(&tmp, bias, &l.bias_dev))) return rc;
   const int nclass = deconv ? 4 : 1;
+  std::vector<float> cls_w[4];
+  const float* ptrs[4] = {nullptr, nullptr, nullptr, nullptr};
   for (int c = 0; c < nclass; ++c) {
-    if (deconv) pack_deconv_class(l, k, c / 2, c % 2, packed); else pack_conv(l, k, packed);
-    if ((rc = upload(&tmp, packed, &l.w_dev[c]))) return rc;
-    if (precision != DEMON_PREC_FP32_SIMT) {
-      ConvProblem p;
-      fill_problem(l, B, p);
-      p.Hi = H; p.Wi = W;
-      if (!deconv) {
-        p.sy = sy; p.sx = sx; p.Ho = bo.H; p.Wo = bo.W; p.Hfull = bo.H; p.Wfull = bo.W; p.ntaps = kh * kw;
-        for (int ky = 0; ky < kh; ++ky)
-          for (int kx = 0; kx < kw; ++kx) { p.dy[ky * kw + kx] = ky - kh / 2; p.dx[ky * kw + kx] = kx - kw / 2; }
-      } else {
-        p.sy = p.sx = 1; p.Ho = H; p.Wo = W; p.Hfull = 2 * H; p.Wfull = 2 * W; p.osy = p.osx = 2; p.ntaps = 4; p.ooy = c / 2; p.oox = c % 2;
-        for (int a = 0; a < 2; ++a)
-          for (int bb = 0; bb < 2; ++bb) { p.dy[a * 2 + bb] = kDeconvD[c / 2][a]; p.dx[a * 2 + bb] = kDeconvD[c % 2][bb]; }
-      }
-      if (!tc_layer_supported(p)) {
-        for (void* q : tmp.dev_allocs) cudaFree(q);
-        return fail(DEMON_E_INVALID, "conv test entry: shape not supported by the tcgen05 path");
-      }
-      if ((rc = tc_layer_prepare(l.tc[c], p, packed.data(), precision))) return rc;
-      l.use_tc = true;
+    if (deconv) pack_deconv_class(l, k, c / 2, c % 2, cls_w[c]); else pack_conv(l, k, cls_w[c]);
+    ptrs[c] = cls_w[c].data();
+    if ((rc = upload(&tmp, cls_w[c], &l.w_dev[c]))) return rc;
+  }
+  if (precision != DEMON_PREC_FP32_SIMT) {
+    ConvProblem probs[4];
+    build_problems(l, B, probs);
+    bool all = true;
+    for (int c = 0; c < nclass; ++c) all = all && tc_layer_supported(probs[c]);
+    if (!all) {
+      for (void* q : tmp.dev_allocs) cudaFree(q);
+      return fail(DEMON_E_INVALID, "conv test entry: shape not supported by the tcgen05 path");
     }
+    if ((rc = tc_layer_prepare(l.tc, probs, ptrs, nclass, precision))) return rc;
+    l.use_tc = true;
   }
   rc = run_layer(l, B, (cudaStream_t)stream);
   cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
   for (void* q : tmp.dev_allocs) cudaFree(q);
-  for (int c = 0; c < 4; ++c) tc_layer_free(l.tc[c]);
+  tc_layer_free(l.tc);
   if (rc) return rc;
   if (e != cudaSuccess) return fail(DEMON_E_CUDA, "conv test entry: %s", cudaGetErrorString(e));
   return DEMON_OK;
