@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "conv_tc.cuh"
+#include "conv_tc_ptx.cuh"
 
 namespace demon {
 
@@ -29,7 +30,6 @@ namespace {
 
 constexpr int kThreads = 320;
 constexpr int kATileBytes = 128 * 128;   // 128 rows x 32 fp32
-constexpr long long kTimeoutCycles = 4000000000ll;   // ~2 s at 1.9 GHz
 
 struct TcParams {
   // tiling of the output index space
@@ -58,122 +58,6 @@ struct TcParams {
   int leaky;
   int* err;
 };
-
-// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes) : "memory");
-}
-// Bounded wait: a pipeline bug must not hang the GPU; on timeout the error flag is raised and the kernel runs to
-// completion with garbage (the host checks the flag in tests).
-__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n.reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n}"
-      : "=r"(done)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return done != 0;
-}
-__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, int* err) {
-  const long long t0 = clock64();
-  for (;;) {
-    for (int i = 0; i < 64; ++i)
-      if (mbar_try(bar, parity)) return true;
-    if (*reinterpret_cast<volatile int*>(err) != 0) return false;   // somebody already timed out: drain quickly
-    if (clock64() - t0 > kTimeoutCycles) {
-      atomicExch(err, 1);
-      return false;
-    }
-  }
-}
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err) {
-  if (mbar_try(bar, parity)) return true;
-  return mbar_wait_slow(bar, parity, err);
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], kind::tf32, issued by one thread
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// arrives on the mbarrier once all previously issued MMAs of this thread have completed
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// Shared-memory matrix descriptor, K-major operand with 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes
-// apart (SBO), descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.  (cute/arch/mma_sm100_desc.hpp)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);   // start address, bits [0,14)
-  d |= (uint64_t)0 << 16;                        // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset, bits [32,46)
-  d |= (uint64_t)1 << 46;                        // version
-  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
-  return d;
-}
-
-// Instruction descriptor for kind::tf32, fp32 accumulate, A and B K-major, M = 128 (cute/arch/mma_sm100_desc.hpp)
-__device__ __forceinline__ uint32_t umma_idesc_tf32(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
 
 __device__ __forceinline__ void decode_tile(const TcParams& p, int tile, int& cls, int& nt, int& n0, int& y0, int& x0) {
   nt = tile % p.n_tiles;
@@ -258,21 +142,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.n_tile);
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(full0 + 8 * stage, phase, p.err);
-          if (p.nsplit == 3) mbar_wait(split0 + 8 * stage, phase, p.err);
           tc_fence_after();
           const uint32_t sbase = smem_u32(smem + (size_t)stage * p.stage_bytes);
           const uint64_t a_hi = umma_desc_sw128(sbase), a_lo = umma_desc_sw128(sbase + kATileBytes);
           const uint64_t w_hi = umma_desc_sw128(sbase + 2 * kATileBytes), w_lo = umma_desc_sw128(sbase + 2 * kATileBytes + w_half);
+          // the two products on the raw A image go first: they overlap the splitter warps' work on A_lo
 #pragma unroll
           for (int j = 0; j < 4; ++j) {   // 4 x K8 = 32 channels; +32 bytes per K8 step inside the swizzled row
             const uint64_t adv = (uint64_t)(2 * j);
-            if (p.nsplit == 3) {
-              umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, (ks | j) != 0);
-              umma_tf32(d_tmem, a_lo + adv, w_hi + adv, idesc, 1);
-              umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, 1);
-            } else {
-              umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, (ks | j) != 0);
-            }
+            if (p.nsplit == 3) umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, (ks | j) != 0);
+            umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, (p.nsplit == 3) ? 1u : (uint32_t)((ks | j) != 0));
+          }
+          if (p.nsplit == 3) {
+            mbar_wait(split0 + 8 * stage, phase, p.err);
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) umma_tf32(d_tmem, a_lo + (uint64_t)(2 * j), w_hi + (uint64_t)(2 * j), idesc, 1);
           }
           umma_commit(empty0 + 8 * stage);                 // frees the smem stage when these MMAs are done
           if (ks == ksteps - 1) umma_commit(afull0 + 8 * a);   // accumulator complete
@@ -290,18 +175,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(full0 + 8 * stage, phase, p.err);
           __syncwarp();
-          const float4* src = reinterpret_cast<const float4*>(smem + (size_t)stage * p.stage_bytes);
-          float4* dst = reinterpret_cast<float4*>(smem + (size_t)stage * p.stage_bytes + kATileBytes);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 v = src[t + 128 * j];
-            float4 r;
-            r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-            r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-            r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-            r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-            dst[t + 128 * j] = r;
-          }
+          const uint32_t sb = smem_u32(smem + (size_t)stage * p.stage_bytes);
+          split_region(sb, sb + kATileBytes, kATileBytes / 16, t);
           fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
           __syncwarp();
           if (lane == 0) mbar_arrive(split0 + 8 * stage);
@@ -514,6 +389,7 @@ int tc_layer_prepare(TcLayer& t, const ConvProblem* probs, const float* const* w
 }
 
 void tc_layer_free(TcLayer& t) {
+  tc_halo_free(t);
   if (t.w_packed) cudaFree(t.w_packed);
   t.w_packed = nullptr;
 }

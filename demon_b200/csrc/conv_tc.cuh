@@ -18,6 +18,7 @@ struct TcLayer {
   int stages = 0;
   int smem_bytes = 0;
   unsigned char tmap_host[128];
+  void* halo_plan = nullptr;  // non-null: the layer runs on the halo kernel (conv_tc_halo.cu); owned
 };
 
 bool tc_layer_supported(const ConvProblem& p);
@@ -27,6 +28,11 @@ bool tc_layer_supported(const ConvProblem& p);
 int tc_layer_prepare(TcLayer& t, const ConvProblem* probs, const float* const* w_hosts, int nclass, int precision);
 void tc_layer_free(TcLayer& t);
 int conv_tc_launch(const TcLayer& t, const ConvProblem* probs, cudaStream_t stream);
+// Halo variant (conv_tc_halo.cu): one fetch of every input pixel per output tile; for layers made of whole 16x8 tiles.
+bool tc_halo_supported(const ConvProblem* probs, int nclass);
+int tc_halo_prepare(TcLayer& t, const ConvProblem* probs, const float* const* w_hosts, int nclass, int precision);
+void tc_halo_free(TcLayer& t);
+int conv_tc_halo_launch(const TcLayer& t, const ConvProblem* probs, cudaStream_t stream);
 // 1 if any mbarrier wait of the tcgen05 kernel has timed out since process start (pipeline bug detector)
 int tc_read_error_flag();
 

@@ -1,0 +1,524 @@
+// tcgen05 implicit-GEMM convolution, "halo" variant: every input pixel is fetched ONCE per output tile.
+//
+// conv_tc.cu fetches one shifted 128-pixel A tile per filter tap, i.e. it reads the input kh*kw times (16 times for the
+// four sub-pixel classes of a transposed convolution) and splits it into hi/lo as often; at the resolutions of the
+// first and last layers that makes the kernel L2-bandwidth bound.  Here the output tile is 16 rows x 8 columns and,
+// per 32-channel chunk, ONE TMA box per stride-parity plane brings the tile plus its halo into shared memory
+// ((16+nqy-1) x (8+nqx-1) pixels, 128 bytes per pixel, 128-byte swizzle).  Every tap is then just a different START
+// ADDRESS of the same shared-memory image:
+//
+//     MMA row m = (y, x) of the tile  ->  halo pixel (y + qy - qy_min, x + qx - qx_min)
+//     descriptor start = plane + ((qy - qy_min) * cols + (qx - qx_min)) * 128,   stride byte offset = cols * 128
+//
+// which works because the tensor core applies the 128-byte swizzle on ABSOLUTE shared-memory address bits: a start
+// address shifted by whole 128-byte rows and a stride that is not a multiple of 1024 read exactly the expected rows
+// (measured with tools/umma_shift_probe.cu; the descriptor's base_offset field must stay 0).  The 8 rows of a swizzle
+// atom are 8 horizontally adjacent pixels, the 16 atoms of an M = 128 operand are the 16 tile rows.
+//
+// Weights stream through their own ring, one block per (chunk, tap); all sub-pixel classes of a transposed convolution
+// accumulate side by side in TMEM (nclass x N columns, double buffered), so the input halo is shared by all 16 taps.
+// Everything else (3xTF32 split by the splitter warps, persistent tiles, warp roles, bounded waits) is as in conv_tc.cu.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "conv_tc.cuh"
+#include "conv_tc_ptx.cuh"
+
+namespace demon {
+
+namespace {
+
+constexpr int kThreads = 352;   // 11 warps: A producer, MMA, 4 splitters, 4 epilogue, W producer
+constexpr int kMaxAStages = 3;
+constexpr int kTileH = 16, kTileW = 8;
+constexpr int kMaxPlanes = 4;
+constexpr int kMaxWStages = 8;
+
+struct HaloPlane {
+  int c_off;      // coordinate offset in dim 0 (rx * in_pitch)
+  int ry;         // coordinate in dim 2
+  int qx_min, qy_min;
+  int cols, rows; // halo box
+  int smem_off;   // byte offset of the plane inside the A region (1024-aligned)
+  int bytes;      // rows * cols * 128
+};
+
+struct HaloTap {
+  int plane;
+  int a_off;      // byte offset of the tap's first pixel inside its plane
+  int cls;
+  int first;      // 1: first tap of its class (accumulator starts from zero at chunk 0)
+};
+
+struct HaloParams {
+  int tiles_x, tiles_y, B, n_tiles, total_tiles;
+  int k_chunks, nplanes, ntaps, nclass;
+  HaloPlane planes[kMaxPlanes];
+  HaloTap taps[kMaxTaps];
+  int a_region_bytes;   // hi image of all planes (lo image follows at the same offsets)
+  int sa;               // A stages
+  int w_stage_bytes, sw;
+  int n_tile, nsplit, tmem_cols;
+  const unsigned char* w;
+  float* out;
+  int out_pitch, Ho, Wo, Hfull, Wfull, osy, osx, Cout;
+  int cls_ooy[4], cls_oox[4];
+  const float* bias;
+  int leaky;
+  int* err;
+};
+
+struct HaloMaps {
+  CUtensorMap m[kMaxPlanes];
+};
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ void halo_decode_tile(const HaloParams& p, int tile, int& nt, int& n, int& y0, int& x0) {
+  nt = tile % p.n_tiles;
+  int m = tile / p.n_tiles;
+  const int xb = m % p.tiles_x;
+  m /= p.tiles_x;
+  const int yb = m % p.tiles_y;
+  n = m / p.tiles_y;
+  y0 = yb * kTileH; x0 = xb * kTileW;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // bars: A_full[3], A_split[3], A_empty[3], W_full[8], W_empty[8], accum_full[2], accum_empty[2]
+  __shared__ __align__(8) uint64_t bars[3 * kMaxAStages + 2 * kMaxWStages + 4];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t afull0 = smem_u32(&bars[0]), asplit0 = smem_u32(&bars[kMaxAStages]), aempty0 = smem_u32(&bars[2 * kMaxAStages]);
+  const uint32_t wfull0 = smem_u32(&bars[3 * kMaxAStages]), wempty0 = smem_u32(&bars[3 * kMaxAStages + kMaxWStages]);
+  const uint32_t cfull0 = smem_u32(&bars[3 * kMaxAStages + 2 * kMaxWStages]), cempty0 = smem_u32(&bars[3 * kMaxAStages + 2 * kMaxWStages + 2]);
+  const int a_stage_bytes = 2 * p.a_region_bytes;
+  unsigned char* w_ring = smem + (size_t)p.sa * a_stage_bytes;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.nplanes; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[i]) : "memory");
+    for (int s = 0; s < kMaxAStages; ++s) {
+      mbar_init(afull0 + 8 * s, 1);
+      mbar_init(asplit0 + 8 * s, 4);
+      mbar_init(aempty0 + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(cfull0 + 8 * s, 1);
+      mbar_init(cempty0 + 8 * s, 4);
+    }
+    for (int s = 0; s < kMaxWStages; ++s) {
+      mbar_init(wfull0 + 8 * s, 1);
+      mbar_init(wempty0 + 8 * s, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  const int acc_cols = p.nclass * p.n_tile;   // columns of one accumulator buffer
+
+  if (warp == 0) {
+    // ===== A producer: one halo box per plane and 32-channel chunk ======================================================
+    if (lane == 0) {
+      int sa = 0;
+      uint32_t pa = 0;
+      uint32_t a_bytes = 0;
+      for (int i = 0; i < p.nplanes; ++i) a_bytes += (uint32_t)p.planes[i].bytes;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int nt, n, y0, x0;
+        halo_decode_tile(p, tile, nt, n, y0, x0);
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(aempty0 + 8 * sa, pa ^ 1, p.err);
+          const uint32_t abase = smem_u32(smem + (size_t)sa * a_stage_bytes);
+          mbar_expect_tx(afull0 + 8 * sa, a_bytes);
+          for (int i = 0; i < p.nplanes; ++i) {
+            const HaloPlane& pl = p.planes[i];
+            tma_load_5d(abase + pl.smem_off, &maps.m[i], afull0 + 8 * sa, pl.c_off + kc * 32, x0 + pl.qx_min, pl.ry, y0 + pl.qy_min, n);
+          }
+          if (++sa == p.sa) { sa = 0; pa ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ===== W producer: one weight block per (chunk, tap), its own ring so that it never holds back the halo loads =======
+    if (lane == 0) {
+      int sw = 0;
+      uint32_t pw = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        const unsigned char* wsrc = p.w + (size_t)nt * p.k_chunks * p.ntaps * p.w_stage_bytes;
+        for (int kt = 0; kt < p.k_chunks * p.ntaps; ++kt) {
+          mbar_wait(wempty0 + 8 * sw, pw ^ 1, p.err);
+          mbar_expect_tx(wfull0 + 8 * sw, (uint32_t)p.w_stage_bytes);
+          bulk_load(smem_u32(w_ring + (size_t)sw * p.w_stage_bytes), wsrc + (size_t)kt * p.w_stage_bytes, (uint32_t)p.w_stage_bytes,
+                    wfull0 + 8 * sw);
+          if (++sw == p.sw) { sw = 0; pw ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer ====================================================================================================
+    if (lane == 0) {
+      int sa = 0, sw = 0;
+      uint32_t pa = 0, pw = 0;
+      const uint32_t idesc = umma_idesc_tf32(p.n_tile);
+      const uint32_t w_half = (uint32_t)p.n_tile * 128u;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int a = it & 1;
+        mbar_wait(cempty0 + 8 * a, ((it >> 1) & 1) ^ 1, p.err);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + (uint32_t)(a * acc_cols);
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(afull0 + 8 * sa, pa, p.err);
+          tc_fence_after();
+          bool split_ready = (p.nsplit != 3);
+          const uint32_t abase = smem_u32(smem + (size_t)sa * a_stage_bytes);
+          for (int t = 0; t < p.ntaps; ++t) {
+            const HaloTap& tp = p.taps[t];
+            const HaloPlane& pl = p.planes[tp.plane];
+            mbar_wait(wfull0 + 8 * sw, pw, p.err);
+            tc_fence_after();
+            const uint32_t a_addr = abase + pl.smem_off + tp.a_off;
+            const uint32_t sbo = (uint32_t)pl.cols * 128u;
+            const uint64_t a_hi = umma_desc_sw128_sbo(a_addr, sbo), a_lo = umma_desc_sw128_sbo(a_addr + p.a_region_bytes, sbo);
+            const uint32_t wbase = smem_u32(w_ring + (size_t)sw * p.w_stage_bytes);
+            const uint64_t w_hi = umma_desc_sw128_sbo(wbase, 1024), w_lo = umma_desc_sw128_sbo(wbase + w_half, 1024);
+            const uint32_t d_tmem = d_base + (uint32_t)(tp.cls * p.n_tile);
+            const bool fresh = (kc == 0) && tp.first;
+            // the two products on the raw halo image first; the lo image is only needed for the third
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint64_t adv = (uint64_t)(2 * j);
+              if (p.nsplit == 3) umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, !(fresh && j == 0));
+              umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, (p.nsplit == 3) ? 1u : (uint32_t)!(fresh && j == 0));
+            }
+            if (p.nsplit == 3) {
+              if (!split_ready) {
+                mbar_wait(asplit0 + 8 * sa, pa, p.err);
+                tc_fence_after();
+                split_ready = true;
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) umma_tf32(d_tmem, a_lo + (uint64_t)(2 * j), w_hi + (uint64_t)(2 * j), idesc, 1);
+            }
+            umma_commit(wempty0 + 8 * sw);
+            if (++sw == p.sw) { sw = 0; pw ^= 1; }
+          }
+          umma_commit(aempty0 + 8 * sa);
+          if (kc == p.k_chunks - 1) umma_commit(cfull0 + 8 * a);
+          if (++sa == p.sa) { sa = 0; pa ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ===== splitters: lo image = A - trunc_tf32(A) over the whole halo region ===========================================
+    if (p.nsplit == 3) {
+      const int t = threadIdx.x - 64;
+      const int nvec = p.a_region_bytes >> 4;
+      int sa = 0;
+      uint32_t pa = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          mbar_wait(afull0 + 8 * sa, pa, p.err);
+          __syncwarp();
+          const uint32_t sb = smem_u32(smem + (size_t)sa * a_stage_bytes);
+          split_region(sb, sb + (uint32_t)p.a_region_bytes, nvec, t);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(asplit0 + 8 * sa);
+          if (++sa == p.sa) { sa = 0; pa ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 10) {
+    // ===== epilogue ======================================================================================================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int yl = m >> 3, xl = m & 7;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      int nt, n, y0, x0;
+      halo_decode_tile(p, tile, nt, n, y0, x0);
+      const int a = it & 1;
+      mbar_wait(cfull0 + 8 * a, (it >> 1) & 1, p.err);
+      __syncwarp();
+      tc_fence_after();
+      const int oy = y0 + yl, ox = x0 + xl;
+      const bool valid = oy < p.Ho && ox < p.Wo;
+      const int cbase = nt * p.n_tile;
+      for (int cls = 0; cls < p.nclass; ++cls) {
+        float* orow = p.out + ((size_t)(n * p.Hfull + oy * p.osy + p.cls_ooy[cls]) * p.Wfull + ox * p.osx + p.cls_oox[cls]) * p.out_pitch;
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * acc_cols + cls * p.n_tile);
+        for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+          uint32_t v[32];
+          const int ncol = (p.n_tile - c0) >= 32 ? 32 : 16;
+          if (ncol == 32) tmem_ld_x32(t_row + c0, v); else tmem_ld_x16(t_row + c0, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const int col = cbase + c0 + 4 * g;
+              if (4 * g < ncol && col < p.Cout) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+                float4 o;
+                o.x = __uint_as_float(v[4 * g + 0]) + b.x;
+                o.y = __uint_as_float(v[4 * g + 1]) + b.y;
+                o.z = __uint_as_float(v[4 * g + 2]) + b.z;
+                o.w = __uint_as_float(v[4 * g + 3]) + b.w;
+                if (p.leaky) {
+                  o.x = fmaxf(0.1f * o.x, o.x); o.y = fmaxf(0.1f * o.y, o.y);
+                  o.z = fmaxf(0.1f * o.z, o.z); o.w = fmaxf(0.1f * o.w, o.w);
+                }
+                *reinterpret_cast<float4*>(orow + col) = o;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(cempty0 + 8 * a);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+int floor_div_h(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+}  // namespace
+
+// ---- host side ------------------------------------------------------------------------------------------------------
+struct HaloPlan {
+  HaloParams prm;
+  HaloMaps maps;
+  int smem_bytes;
+};
+
+static bool halo_build(const ConvProblem* probs, int nclass, int n_tile_req, int nsplit, HaloPlan& plan, bool encode) {
+  const ConvProblem& p = probs[0];
+  HaloParams& prm = plan.prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.nclass = nclass;
+  prm.nsplit = nsplit;
+  // planes: taps grouped by stride parity
+  struct PInfo { int ry, rx, qy_min, qy_max, qx_min, qx_max; };
+  std::vector<PInfo> pinfo;
+  struct TInfo { int plane, qy, qx, cls; };
+  std::vector<TInfo> tinfo;
+  for (int c = 0; c < nclass; ++c)
+    for (int i = 0; i < probs[c].ntaps; ++i) {
+      const int qy = floor_div_h(probs[c].dy[i], p.sy), ry = probs[c].dy[i] - qy * p.sy;
+      const int qx = floor_div_h(probs[c].dx[i], p.sx), rx = probs[c].dx[i] - qx * p.sx;
+      int pi = -1;
+      for (size_t k = 0; k < pinfo.size(); ++k)
+        if (pinfo[k].ry == ry && pinfo[k].rx == rx) pi = (int)k;
+      if (pi < 0) { pinfo.push_back({ry, rx, qy, qy, qx, qx}); pi = (int)pinfo.size() - 1; }
+      PInfo& pl = pinfo[pi];
+      pl.qy_min = std::min(pl.qy_min, qy); pl.qy_max = std::max(pl.qy_max, qy);
+      pl.qx_min = std::min(pl.qx_min, qx); pl.qx_max = std::max(pl.qx_max, qx);
+      tinfo.push_back({pi, qy, qx, c});
+    }
+  if ((int)pinfo.size() > kMaxPlanes || (int)tinfo.size() > kMaxTaps) return false;
+  prm.nplanes = (int)pinfo.size();
+  prm.ntaps = (int)tinfo.size();
+  int off = 0;
+  for (int i = 0; i < prm.nplanes; ++i) {
+    HaloPlane& pl = prm.planes[i];
+    pl.c_off = pinfo[i].rx * p.in_pitch; pl.ry = pinfo[i].ry;
+    pl.qx_min = pinfo[i].qx_min; pl.qy_min = pinfo[i].qy_min;
+    pl.cols = kTileW + pinfo[i].qx_max - pinfo[i].qx_min;
+    pl.rows = kTileH + pinfo[i].qy_max - pinfo[i].qy_min;
+    if (pl.cols > 256 || pl.rows > 256) return false;
+    pl.bytes = pl.rows * pl.cols * 128;
+    pl.smem_off = off;
+    off += (pl.bytes + 1023) / 1024 * 1024;
+  }
+  prm.a_region_bytes = off;
+  int last_cls = -1;
+  for (int t = 0; t < prm.ntaps; ++t) {
+    HaloTap& tp = prm.taps[t];
+    const HaloPlane& pl = prm.planes[tinfo[t].plane];
+    tp.plane = tinfo[t].plane;
+    tp.a_off = ((tinfo[t].qy - pl.qy_min) * pl.cols + (tinfo[t].qx - pl.qx_min)) * 128;
+    tp.cls = tinfo[t].cls;
+    tp.first = (tp.cls != last_cls) ? 1 : 0;
+    last_cls = tp.cls;
+  }
+  // N tile: all classes accumulate side by side, double buffered, in 512 TMEM columns
+  const int cout16 = (p.Cout + 15) / 16 * 16;
+  int n_tile = std::min(cout16, 256);
+  const int max_n = (512 / (2 * nclass)) / 16 * 16;
+  n_tile = std::min(n_tile, max_n);
+  if (n_tile_req > 0) n_tile = std::min(n_tile, n_tile_req);
+  if (n_tile < 16) return false;
+  prm.n_tile = n_tile;
+  prm.n_tiles = ceil_div(p.Cout, n_tile);
+  int cols = 32;
+  while (cols < 2 * nclass * n_tile) cols <<= 1;
+  prm.tmem_cols = cols;
+  prm.k_chunks = p.Cin / 32;
+  // weight ring slot = one (chunk, tap) block: [W_hi | W_lo] (3xTF32) or W_hi alone, 1024-byte aligned
+  const int slot = (nsplit == 3) ? n_tile * 256 : (n_tile * 128 + 1023) / 1024 * 1024;
+  prm.w_stage_bytes = slot;
+  // shared memory: two A stages (a layer that cannot double-buffer its halo goes to the per-tap kernel), the rest for
+  // the weight ring
+  const int budget = 224 * 1024;
+  prm.sa = 3;
+  if (budget - prm.sa * 2 * prm.a_region_bytes < 4 * slot) prm.sa = 2;
+  const int rest = budget - prm.sa * 2 * prm.a_region_bytes;
+  if (rest < 2 * slot) return false;
+  prm.sw = std::min(kMaxWStages, rest / slot);
+  plan.smem_bytes = prm.sa * 2 * prm.a_region_bytes + prm.sw * slot + 1024;
+  prm.tiles_x = ceil_div(p.Wo, kTileW); prm.tiles_y = ceil_div(p.Ho, kTileH); prm.B = p.B;
+  prm.total_tiles = prm.tiles_x * prm.tiles_y * p.B * prm.n_tiles;
+  prm.out = p.out; prm.out_pitch = p.out_pitch; prm.Ho = p.Ho; prm.Wo = p.Wo; prm.Hfull = p.Hfull; prm.Wfull = p.Wfull;
+  prm.osy = p.osy; prm.osx = p.osx; prm.Cout = p.Cout; prm.bias = p.bias; prm.leaky = p.leaky;
+  for (int c = 0; c < nclass; ++c) { prm.cls_ooy[c] = probs[c].ooy; prm.cls_oox[c] = probs[c].oox; }
+  if (!encode) return true;
+  // TMA descriptors: same 5-D view as conv_tc.cu, one box shape per plane
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fp = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+    return false;
+  EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(fp);
+  const cuuint64_t cp = (cuuint64_t)p.in_pitch;
+  cuuint64_t gdim[5] = {(cuuint64_t)(p.sx - 1) * cp + (cuuint64_t)p.Cin, (cuuint64_t)(p.Wi / p.sx), (cuuint64_t)p.sy,
+                        (cuuint64_t)(p.Hi / p.sy), (cuuint64_t)p.B};
+  cuuint64_t gstr[4] = {(cuuint64_t)p.sx * cp * 4, (cuuint64_t)p.Wi * cp * 4, (cuuint64_t)p.sy * p.Wi * cp * 4,
+                        (cuuint64_t)p.Hi * p.Wi * cp * 4};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < prm.nplanes; ++i) {
+    cuuint32_t box[5] = {32, (cuuint32_t)prm.planes[i].cols, 1, (cuuint32_t)prm.planes[i].rows, 1};
+    CUresult r = enc(&plan.maps.m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(p.in), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+  }
+  for (int i = prm.nplanes; i < kMaxPlanes; ++i) plan.maps.m[i] = plan.maps.m[0];
+  return true;
+}
+
+bool tc_halo_supported(const ConvProblem* probs, int nclass) {
+  const ConvProblem& p = probs[0];
+  for (int c = 0; c < nclass; ++c)
+    if (!tc_layer_supported(probs[c])) return false;
+  if ((p.Ho % kTileH) != 0 || (p.Wo % kTileW) != 0) return false;   // whole tiles only; other layers use the per-tap kernel
+  HaloPlan plan;
+  return halo_build(probs, nclass, 0, 3, plan, false);
+}
+
+static float tf32_round_h(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return x;
+  u += 0x00000FFFu + ((u >> 13) & 1u);
+  u &= 0xFFFFE000u;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+
+int tc_halo_prepare(TcLayer& t, const ConvProblem* probs, const float* const* w_hosts, int nclass, int precision) {
+  const ConvProblem& p = probs[0];
+  const int nsplit = (precision == DEMON_PREC_TF32) ? 1 : 3;
+  HaloPlan* plan = new HaloPlan();
+  if (!halo_build(probs, nclass, 0, nsplit, *plan, true)) {
+    delete plan;
+    return fail(DEMON_E_CUDA, "tc_halo_prepare: could not build the plan (tensor map encode failed?)");
+  }
+  const HaloParams& prm = plan->prm;
+  // weights: [n_tile][chunk][tap (class major)] blocks of [W_hi | W_lo], n_tile rows x 32 fp32, K-major, pre-swizzled
+  const int slot = prm.w_stage_bytes;
+  const size_t total = (size_t)prm.n_tiles * prm.k_chunks * prm.ntaps * slot;
+  std::vector<unsigned char> packed(total, 0);
+  std::vector<int> tap_in_class(prm.ntaps);
+  {
+    int cnt[4] = {0, 0, 0, 0};
+    for (int tt = 0; tt < prm.ntaps; ++tt) tap_in_class[tt] = cnt[prm.taps[tt].cls]++;
+  }
+  for (int nt = 0; nt < prm.n_tiles; ++nt)
+    for (int kc = 0; kc < prm.k_chunks; ++kc)
+      for (int tt = 0; tt < prm.ntaps; ++tt) {
+        unsigned char* blk = packed.data() + ((size_t)(nt * prm.k_chunks + kc) * prm.ntaps + tt) * slot;
+        const int cls = prm.taps[tt].cls, tap = tap_in_class[tt];
+        for (int r = 0; r < prm.n_tile; ++r) {
+          const int co = nt * prm.n_tile + r;
+          for (int k = 0; k < 32; ++k) {
+            float w = 0.f;
+            if (co < p.Cout) w = w_hosts[cls][((size_t)tap * p.Cin + kc * 32 + k) * p.Cout_pad + co];
+            const float hi = (nsplit == 3) ? tf32_round_h(w) : w;
+            const float lo = w - hi;
+            const size_t off = (size_t)r * 128 + (size_t)(((k >> 2) ^ (r & 7)) << 4) + (size_t)(k & 3) * 4;
+            memcpy(blk + off, &hi, 4);
+            if (nsplit == 3) memcpy(blk + (size_t)prm.n_tile * 128 + off, &lo, 4);
+          }
+        }
+      }
+  void* dw = nullptr;
+  cudaError_t e = cudaMalloc(&dw, total);
+  if (e == cudaSuccess) e = cudaMemcpy(dw, packed.data(), total, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { delete plan; return fail(DEMON_E_CUDA, "tc_halo_prepare: %s", cudaGetErrorString(e)); }
+  plan->prm.w = static_cast<const unsigned char*>(dw);
+  t.w_packed = dw;
+  t.halo_plan = plan;
+  t.nclass = nclass;
+  t.n_tile = prm.n_tile; t.n_tiles = prm.n_tiles; t.k_chunks = prm.k_chunks; t.nsplit = nsplit;
+  t.th = kTileH; t.tw = kTileW; t.tb = 1; t.stages = prm.sa; t.smem_bytes = plan->smem_bytes;
+  return DEMON_OK;
+}
+
+void tc_halo_free(TcLayer& t) {
+  if (t.halo_plan) delete static_cast<HaloPlan*>(t.halo_plan);
+  t.halo_plan = nullptr;
+}
+
+extern int* tc_error_flag();
+
+int conv_tc_halo_launch(const TcLayer& t, const ConvProblem* probs, cudaStream_t stream) {
+  HaloPlan* plan = static_cast<HaloPlan*>(t.halo_plan);
+  HaloParams prm = plan->prm;
+  prm.out = probs[0].out;          // the output slice may be re-pointed between calls (caller-owned result buffers)
+  prm.out_pitch = probs[0].out_pitch;
+  prm.err = tc_error_flag();
+  static bool attr_set = false;
+  if (!attr_set) {
+    DEMON_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    attr_set = true;
+  }
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  const int grid = std::min(prm.total_tiles, sms);
+  conv_tc_halo_kernel<<<grid, kThreads, plan->smem_bytes, stream>>>(plan->maps, prm);
+  DEMON_LAUNCH_CHECK();
+  return DEMON_OK;
+}
+
+}  // namespace demon

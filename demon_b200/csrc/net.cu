@@ -6,6 +6,7 @@
 // geometry ops between the blocks (blocks_original.py:155-187,336-366) run as two fused glue kernels
 // that produce the `conv2_extra_inputs` tensor directly, and nothing on the forward path allocates,
 // synchronises or touches the host.
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -321,6 +322,12 @@ void fill_problem(const Layer& l, int B, ConvProblem& p) {
   p.osy = p.osx = 1;
 }
 
+// DEMON_TC_HALO=0 keeps every tensor-core layer on the per-tap kernel (A/B measurements)
+bool use_halo_kernel() {
+  const char* e = getenv("DEMON_TC_HALO");
+  return !(e && e[0] == '0');
+}
+
 // The convolution problem(s) of a layer: 1 for conv / dense, 4 sub-pixel classes for a transposed conv.
 int build_problems(const Layer& l, int B, ConvProblem* out) {
   ConvProblem p;
@@ -367,7 +374,7 @@ int build_problems(const Layer& l, int B, ConvProblem* out) {
 int run_layer(const Layer& l, int B, cudaStream_t stream, float* splitk_ws = nullptr) {
   ConvProblem probs[4];
   const int nclass = build_problems(l, B, probs);
-  if (l.use_tc) return conv_tc_launch(l.tc, probs, stream);
+  if (l.use_tc) return l.tc.halo_plan ? conv_tc_halo_launch(l.tc, probs, stream) : conv_tc_launch(l.tc, probs, stream);
   for (int c = 0; c < nclass; ++c) {
     if (l.kind == L_DENSE && l.ksplit > 1 && splitk_ws) { probs[c].partial = splitk_ws; probs[c].ksplit = l.ksplit; }
     int rc = conv_simt_launch(probs[c], stream);
@@ -747,7 +754,9 @@ int demon_net_finalize(demon_net* n) {
           if (l.kind == L_CONV) pack_conv(l, k, cls_w[c]); else pack_deconv_class(l, k, c / 2, c % 2, cls_w[c]);
           ptrs[c] = cls_w[c].data();
         }
-        if ((rc = tc_layer_prepare(l.tc, probs, ptrs, nclass, n->precision))) return rc;
+        if (use_halo_kernel() && tc_halo_supported(probs, nclass)) rc = tc_halo_prepare(l.tc, probs, ptrs, nclass, n->precision);
+        else rc = tc_layer_prepare(l.tc, probs, ptrs, nclass, n->precision);
+        if (rc) return rc;
         l.use_tc = true;
       }
     }
@@ -961,7 +970,9 @@ static int standalone_conv(const float* in, float* out, int B, int H, int W, int
       for (void* q : tmp.dev_allocs) cudaFree(q);
       return fail(DEMON_E_INVALID, "conv test entry: shape not supported by the tcgen05 path");
     }
-    if ((rc = tc_layer_prepare(l.tc, probs, ptrs, nclass, precision))) return rc;
+    if (use_halo_kernel() && tc_halo_supported(probs, nclass)) rc = tc_halo_prepare(l.tc, probs, ptrs, nclass, precision);
+    else rc = tc_layer_prepare(l.tc, probs, ptrs, nclass, precision);
+    if (rc) return rc;
     l.use_tc = true;
   }
   rc = run_layer(l, B, (cudaStream_t)stream);

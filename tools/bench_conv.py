@@ -1,0 +1,56 @@
+"""Runs ONE convolution shape of the DeMoN graphs at batch 64 through the C-ABI test entry (for ncu captures)."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from demon_b200 import _lib
+
+SHAPES = {
+    # name: (kind, B, H, W, Cin, Cout, kh, kw, sy, sx)
+    "pd0_conv1": ("conv", 64, 192, 256, 64, 16, 3, 3, 1, 1),
+    "refine_conv1_1": ("conv", 64, 96, 128, 64, 64, 3, 3, 1, 1),
+    "refine_conv2_1": ("conv", 64, 48, 64, 128, 128, 3, 3, 1, 1),
+    "refine0_upconv": ("deconv", 64, 96, 128, 128, 32),
+    "conv1x": ("conv", 64, 96, 256, 32, 32, 1, 9, 1, 2),
+    "predict2_conv1": ("conv", 64, 48, 64, 128, 24, 3, 3, 1, 1),
+    "conv5_1y": ("conv", 64, 6, 8, 512, 512, 3, 1, 1, 1),
+    "conv3x": ("conv", 64, 24, 64, 128, 128, 1, 5, 1, 2),
+    "refine2_upconv": ("deconv", 64, 24, 32, 256, 64),
+}
+
+
+def main():
+    name = sys.argv[1]
+    prec = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+    lib = _lib.load()
+    spec = SHAPES[name]
+    rng = np.random.RandomState(0)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if spec[0] == "conv":
+        _, B, H, W, Cin, Cout, kh, kw, sy, sx = spec
+        x = torch.rand(B, H, W, Cin, device="cuda") - 0.5
+        out = torch.empty(B, -(-H // sy), -(-W // sx), Cout, device="cuda")
+        k = (rng.standard_normal((kh, kw, Cin, Cout)) / np.sqrt(kh * kw * Cin)).astype(np.float32)
+        b = np.zeros(Cout, np.float32)
+        for _ in range(reps):
+            _lib.check(lib.demon_conv2d_nhwc(x.data_ptr(), out.data_ptr(), B, H, W, Cin, Cout, kh, kw, sy, sx, k.ctypes.data, b.ctypes.data, 1, prec, stream))
+    else:
+        _, B, H, W, Cin, Cout = spec
+        x = torch.rand(B, H, W, Cin, device="cuda") - 0.5
+        out = torch.empty(B, 2 * H, 2 * W, Cout, device="cuda")
+        k = (rng.standard_normal((4, 4, Cout, Cin)) / np.sqrt(4 * Cin)).astype(np.float32)
+        b = np.zeros(Cout, np.float32)
+        for _ in range(reps):
+            _lib.check(lib.demon_deconv4x4s2_nhwc(x.data_ptr(), out.data_ptr(), B, H, W, Cin, Cout, k.ctypes.data, b.ctypes.data, 1, prec, stream))
+    torch.cuda.synchronize()
+    print(name, "done; timeouts", lib.demon_debug_tc_timeouts())
+
+
+if __name__ == "__main__":
+    main()

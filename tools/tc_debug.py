@@ -40,6 +40,29 @@ def ref(x, k, b, sy, sx, leaky):
     return y.permute(0, 2, 3, 1).numpy()
 
 
+def run_deconv(x, k, b, leaky, prec):
+    B, H, W, Cin = x.shape
+    Cout = k.shape[2]
+    xin = torch.from_numpy(x).cuda()
+    out = torch.full((B, 2 * H, 2 * W, Cout), float("nan"), device="cuda")
+    kk, bb = np.ascontiguousarray(k, np.float32), np.ascontiguousarray(b, np.float32)
+    rc = lib.demon_deconv4x4s2_nhwc(xin.data_ptr(), out.data_ptr(), B, H, W, Cin, Cout, kk.ctypes.data, bb.ctypes.data, int(leaky), prec,
+                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc != 0:
+        return None, lib.demon_last_error().decode()
+    torch.cuda.synchronize()
+    return out.cpu().numpy(), None
+
+
+def ref_deconv(x, k, b, leaky):
+    xt = torch.from_numpy(x).double().permute(0, 3, 1, 2)
+    kt = torch.from_numpy(k).double().permute(3, 2, 0, 1)
+    y = F.conv_transpose2d(xt, kt, torch.from_numpy(b).double(), stride=2, padding=1)
+    if leaky:
+        y = torch.maximum(0.1 * y, y)
+    return y.permute(0, 2, 3, 1).numpy()
+
+
 def report(name, got, want):
     if got is None:
         print("%-44s ERROR" % name)
@@ -60,6 +83,47 @@ def report(name, got, want):
 
 def main():
     rng = np.random.RandomState(0)
+    halo_cases = [
+        ("HALO 1x1 16x8 Cin32 Cout32", 1, 16, 8, 32, 32, 1, 1, 1, 1),
+        ("HALO 3x1 16x8 Cin32 Cout32", 1, 16, 8, 32, 32, 3, 1, 1, 1),
+        ("HALO 1x3 16x8 Cin32 Cout32", 1, 16, 8, 32, 32, 1, 3, 1, 1),
+        ("HALO 3x3 32x16 Cin64 Cout64", 2, 32, 16, 64, 64, 3, 3, 1, 1),
+        ("HALO 3x3 48x64 Cin128 Cout24", 2, 48, 64, 128, 24, 3, 3, 1, 1),
+        ("HALO 3x3 32x24 Cin64 Cout16", 1, 32, 24, 64, 16, 3, 3, 1, 1),
+        ("HALO 1x9 s2 32x32->32x16 Cin32 Cout32", 2, 32, 32, 32, 32, 1, 9, 1, 2),
+        ("HALO 7x1 s2 64x16->32x16 Cin32 Cout32", 2, 64, 16, 32, 32, 7, 1, 2, 1),
+        ("HALO 1x7 s2 Cin32 Cout32", 1, 16, 32, 32, 32, 1, 7, 1, 2),
+        ("HALO 3x3 Cin64 Cout128 48x64", 1, 48, 64, 64, 128, 3, 3, 1, 1),
+    ]
+    for name, B, H, W, Cin, Cout, kh, kw, sy, sx in halo_cases:
+        x = rng.uniform(-1, 1, (B, H, W, Cin)).astype(np.float32)
+        k = (rng.standard_normal((kh, kw, Cin, Cout)) / np.sqrt(kh * kw * Cin)).astype(np.float32)
+        b = rng.uniform(-0.1, 0.1, Cout).astype(np.float32)
+        want = ref(x, k, b, sy, sx, True)
+        for prec, pname in ((2, "tf32"), (1, "3xtf32")):
+            got, e = run(x, k, b, sy, sx, True, prec)
+            if e:
+                print("%-44s %s" % (name + " " + pname, e))
+                continue
+            report(name + " " + pname, got, want)
+        if lib.demon_debug_tc_timeouts():
+            print("pipeline timeout flagged -- stopping")
+            return
+    for name, B, H, W, Cin, Cout in [("HALO deconv 16x8 Cin32 Cout32", 1, 16, 8, 32, 32), ("HALO deconv 48x64 Cin128 Cout64", 2, 48, 64, 128, 64),
+                                     ("HALO deconv 32x32 Cin128 Cout32", 1, 32, 32, 128, 32), ("v1 deconv 24x32 Cin256 Cout64", 2, 24, 32, 256, 64)]:
+        x = rng.uniform(-1, 1, (B, H, W, Cin)).astype(np.float32)
+        k = (rng.standard_normal((4, 4, Cout, Cin)) / np.sqrt(4 * Cin)).astype(np.float32)
+        b = rng.uniform(-0.1, 0.1, Cout).astype(np.float32)
+        want = ref_deconv(x, k, b, True)
+        for prec, pname in ((2, "tf32"), (1, "3xtf32")):
+            got, e = run_deconv(x, k, b, True, prec)
+            if e:
+                print("%-44s %s" % (name + " " + pname, e))
+                continue
+            report(name + " " + pname, got, want)
+        if lib.demon_debug_tc_timeouts():
+            print("pipeline timeout flagged -- stopping")
+            return
     cases = [
         # name, B,H,W,Cin,Cout,kh,kw,sy,sx
         ("1x1 Cin32 Cout32 128px", 1, 2, 64, 32, 32, 1, 1, 1, 1),
