@@ -49,6 +49,7 @@ PROTOTYPES = {
     "demon_net_layer_name": [_P, c_int],
     "demon_net_layer_profile": [_P, c_int, _P, _P, _P, _P],
     "demon_debug_tc_timeouts": [],
+    "demon_debug_tc_timing": [c_int, _P, c_int],
     "demon_conv2d_nhwc": [_P, _P] + [c_int] * 9 + [_P, _P, c_int, c_int, _P],
     "demon_deconv4x4s2_nhwc": [_P, _P] + [c_int] * 5 + [_P, _P, c_int, c_int, _P],
     "demon_last_error": [],

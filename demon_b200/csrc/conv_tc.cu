@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   if (warp == 0) {
     // ===== TMA producer ==============================================================================================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx = kATileBytes + (uint32_t)p.w_stage_bytes;
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ===== MMA issuer ================================================================================================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t idesc = umma_idesc_tf32(p.n_tile);

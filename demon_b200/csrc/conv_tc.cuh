@@ -33,6 +33,9 @@ bool tc_halo_supported(const ConvProblem* probs, int nclass);
 int tc_halo_prepare(TcLayer& t, const ConvProblem* probs, const float* const* w_hosts, int nclass, int precision);
 void tc_halo_free(TcLayer& t);
 int conv_tc_halo_launch(const TcLayer& t, const ConvProblem* probs, cudaStream_t stream);
+// debug: per-CTA wait-cycle counters of the halo kernel (slots documented in tools/bench_conv.py)
+void tc_halo_enable_timing(bool on);
+int tc_halo_read_timing(long long* host, int nblocks);
 // 1 if any mbarrier wait of the tcgen05 kernel has timed out since process start (pipeline bug detector)
 int tc_read_error_flag();
 

@@ -69,6 +69,7 @@ struct HaloParams {
   const float* bias;
   int leaky;
   int* err;
+  long long* timing;   // optional [gridDim.x][16] wait-cycle counters (debug), nullptr in production
 };
 
 struct HaloMaps {
@@ -82,6 +83,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
+}
+
+__device__ __forceinline__ void wait_t(uint32_t bar, uint32_t parity, int* err, long long& acc, bool timed) {
+  if (!timed) { mbar_wait(bar, parity, err); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity, err);
+  acc += clock64() - t0;
 }
 
 __device__ __forceinline__ void halo_decode_tile(const HaloParams& p, int tile, int& nt, int& n, int& y0, int& x0) {
@@ -132,19 +140,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   const int acc_cols = p.nclass * p.n_tile;   // columns of one accumulator buffer
+  const bool timed = p.timing != nullptr;
 
   if (warp == 0) {
     // ===== A producer: one halo box per plane and 32-channel chunk ======================================================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int sa = 0;
       uint32_t pa = 0;
       uint32_t a_bytes = 0;
+      long long w_aempty = 0;
+      const long long t_begin = clock64();
       for (int i = 0; i < p.nplanes; ++i) a_bytes += (uint32_t)p.planes[i].bytes;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int nt, n, y0, x0;
         halo_decode_tile(p, tile, nt, n, y0, x0);
         for (int kc = 0; kc < p.k_chunks; ++kc) {
-          mbar_wait(aempty0 + 8 * sa, pa ^ 1, p.err);
+          wait_t(aempty0 + 8 * sa, pa ^ 1, p.err, w_aempty, timed);
           const uint32_t abase = smem_u32(smem + (size_t)sa * a_stage_bytes);
           mbar_expect_tx(afull0 + 8 * sa, a_bytes);
           for (int i = 0; i < p.nplanes; ++i) {
@@ -154,46 +165,51 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
           if (++sa == p.sa) { sa = 0; pa ^= 1; }
         }
       }
+      if (timed) { p.timing[blockIdx.x * 16 + 0] = w_aempty; p.timing[blockIdx.x * 16 + 8] = clock64() - t_begin; }
     }
   } else if (warp == 10) {
     // ===== W producer: one weight block per (chunk, tap), its own ring so that it never holds back the halo loads =======
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int sw = 0;
       uint32_t pw = 0;
+      long long w_wempty = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles;
         const unsigned char* wsrc = p.w + (size_t)nt * p.k_chunks * p.ntaps * p.w_stage_bytes;
         for (int kt = 0; kt < p.k_chunks * p.ntaps; ++kt) {
-          mbar_wait(wempty0 + 8 * sw, pw ^ 1, p.err);
+          wait_t(wempty0 + 8 * sw, pw ^ 1, p.err, w_wempty, timed);
           mbar_expect_tx(wfull0 + 8 * sw, (uint32_t)p.w_stage_bytes);
           bulk_load(smem_u32(w_ring + (size_t)sw * p.w_stage_bytes), wsrc + (size_t)kt * p.w_stage_bytes, (uint32_t)p.w_stage_bytes,
                     wfull0 + 8 * sw);
           if (++sw == p.sw) { sw = 0; pw ^= 1; }
         }
       }
+      if (timed) p.timing[blockIdx.x * 16 + 1] = w_wempty;
     }
   } else if (warp == 1) {
     // ===== MMA issuer ====================================================================================================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int sa = 0, sw = 0;
       uint32_t pa = 0, pw = 0;
       const uint32_t idesc = umma_idesc_tf32(p.n_tile);
       const uint32_t w_half = (uint32_t)p.n_tile * 128u;
+      long long w_cempty = 0, w_afull = 0, w_asplit = 0, w_wfull = 0;
+      const long long t_begin = clock64();
       int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int a = it & 1;
-        mbar_wait(cempty0 + 8 * a, ((it >> 1) & 1) ^ 1, p.err);
+        wait_t(cempty0 + 8 * a, ((it >> 1) & 1) ^ 1, p.err, w_cempty, timed);
         tc_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)(a * acc_cols);
         for (int kc = 0; kc < p.k_chunks; ++kc) {
-          mbar_wait(afull0 + 8 * sa, pa, p.err);
+          wait_t(afull0 + 8 * sa, pa, p.err, w_afull, timed);
           tc_fence_after();
           bool split_ready = (p.nsplit != 3);
           const uint32_t abase = smem_u32(smem + (size_t)sa * a_stage_bytes);
           for (int t = 0; t < p.ntaps; ++t) {
             const HaloTap& tp = p.taps[t];
             const HaloPlane& pl = p.planes[tp.plane];
-            mbar_wait(wfull0 + 8 * sw, pw, p.err);
+            wait_t(wfull0 + 8 * sw, pw, p.err, w_wfull, timed);
             tc_fence_after();
             const uint32_t a_addr = abase + pl.smem_off + tp.a_off;
             const uint32_t sbo = (uint32_t)pl.cols * 128u;
@@ -211,7 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
             }
             if (p.nsplit == 3) {
               if (!split_ready) {
-                mbar_wait(asplit0 + 8 * sa, pa, p.err);
+                wait_t(asplit0 + 8 * sa, pa, p.err, w_asplit, timed);
                 tc_fence_after();
                 split_ready = true;
               }
@@ -226,6 +242,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
           if (++sa == p.sa) { sa = 0; pa ^= 1; }
         }
       }
+      if (timed) {
+        long long* tm = p.timing + blockIdx.x * 16;
+        tm[2] = w_cempty; tm[3] = w_afull; tm[4] = w_asplit; tm[5] = w_wfull; tm[9] = clock64() - t_begin;
+      }
     }
   } else if (warp < 6) {
     // ===== splitters: lo image = A - trunc_tf32(A) over the whole halo region ===========================================
@@ -234,9 +254,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
       const int nvec = p.a_region_bytes >> 4;
       int sa = 0;
       uint32_t pa = 0;
+      long long w_safull = 0;
+      const long long t_begin = clock64();
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         for (int kc = 0; kc < p.k_chunks; ++kc) {
-          mbar_wait(afull0 + 8 * sa, pa, p.err);
+          wait_t(afull0 + 8 * sa, pa, p.err, w_safull, timed);
           __syncwarp();
           const uint32_t sb = smem_u32(smem + (size_t)sa * a_stage_bytes);
           split_region(sb, sb + (uint32_t)p.a_region_bytes, nvec, t);
@@ -246,18 +268,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
           if (++sa == p.sa) { sa = 0; pa ^= 1; }
         }
       }
+      if (timed && threadIdx.x == 64) { p.timing[blockIdx.x * 16 + 6] = w_safull; p.timing[blockIdx.x * 16 + 10] = clock64() - t_begin; }
     }
   } else if (warp < 10) {
     // ===== epilogue ======================================================================================================
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int yl = m >> 3, xl = m & 7;
+    long long w_cfull = 0;
+    const long long t_begin = clock64();
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       int nt, n, y0, x0;
       halo_decode_tile(p, tile, nt, n, y0, x0);
       const int a = it & 1;
-      mbar_wait(cfull0 + 8 * a, (it >> 1) & 1, p.err);
+      wait_t(cfull0 + 8 * a, (it >> 1) & 1, p.err, w_cfull, timed);
       __syncwarp();
       tc_fence_after();
       const int oy = y0 + yl, ox = x0 + xl;
@@ -296,6 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(cempty0 + 8 * a);
     }
+    if (timed && threadIdx.x == 192) { p.timing[blockIdx.x * 16 + 7] = w_cfull; p.timing[blockIdx.x * 16 + 11] = clock64() - t_begin; }
   }
 
   tc_fence_before();
@@ -500,12 +526,25 @@ void tc_halo_free(TcLayer& t) {
 
 extern int* tc_error_flag();
 
+static long long* g_timing_dev = nullptr;
+void tc_halo_enable_timing(bool on) {
+  if (on && !g_timing_dev) { cudaMalloc(&g_timing_dev, 256 * 16 * sizeof(long long)); }
+  if (g_timing_dev) cudaMemset(g_timing_dev, 0, 256 * 16 * sizeof(long long));
+  if (!on && g_timing_dev) { cudaFree(g_timing_dev); g_timing_dev = nullptr; }
+}
+int tc_halo_read_timing(long long* host, int nblocks) {
+  if (!g_timing_dev) return -1;
+  cudaMemcpy(host, g_timing_dev, (size_t)nblocks * 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+  return 0;
+}
+
 int conv_tc_halo_launch(const TcLayer& t, const ConvProblem* probs, cudaStream_t stream) {
   HaloPlan* plan = static_cast<HaloPlan*>(t.halo_plan);
   HaloParams prm = plan->prm;
   prm.out = probs[0].out;          // the output slice may be re-pointed between calls (caller-owned result buffers)
   prm.out_pitch = probs[0].out_pitch;
   prm.err = tc_error_flag();
+  prm.timing = g_timing_dev;
   static bool attr_set = false;
   if (!attr_set) {
     DEMON_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));

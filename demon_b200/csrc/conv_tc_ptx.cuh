@@ -125,6 +125,15 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32(int n) {
 }
 
 
+// elect.sync: exactly one lane of the (converged) warp gets `true`.  Unlike `lane == 0`, the compiler then KNOWS the
+// region runs with a single active thread and emits the uniform-datapath instructions (UTCHMMA, UTMALDG, UBLKCP, ...)
+// directly instead of wrapping each one in a per-thread serialisation loop (measured: ~90 cycles per MMA issue).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n.reg .b32 rx;\n.reg .pred px;\nelect.sync rx|px, 0xffffffff;\nselp.b32 %0, 1, 0, px;\n}" : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));

@@ -767,6 +767,11 @@ int demon_net_finalize(demon_net* n) {
 }
 
 int demon_debug_tc_timeouts(void) { return tc_read_error_flag(); }
+int demon_debug_tc_timing(int enable, int64_t* host_out, int nblocks) {
+  if (host_out) return tc_halo_read_timing(reinterpret_cast<long long*>(host_out), nblocks);
+  tc_halo_enable_timing(enable != 0);
+  return 0;
+}
 
 int demon_net_batch(const demon_net* n) { return n ? n->B : 0; }
 int64_t demon_net_workspace_bytes(const demon_net* n) { return n ? (int64_t)(n->ws_floats * sizeof(float)) : 0; }

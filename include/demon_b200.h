@@ -180,6 +180,9 @@ int demon_net_layer_profile(const demon_net* net, int i, double* ms, int64_t* ca
 
 /* 1 if a pipeline wait inside the tcgen05 kernel ever timed out in this process (synchronises the device). */
 int demon_debug_tc_timeouts(void);
+/* debug: host_out == NULL: switch the halo kernel's per-CTA wait-cycle counters on/off; otherwise copy [nblocks][16]
+ * counters of the last launch to host_out. */
+int demon_debug_tc_timing(int enable, int64_t* host_out, int nblocks);
 
 /* Standalone convolution entry used by tests to compare the tcgen05 path with the fp32 SIMT path on
  * the same NHWC tensors.  in [B,H,W,Cin], kernel TF layout [kh,kw,cin,cout] (host), bias [cout] (host)

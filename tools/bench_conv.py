@@ -32,6 +32,9 @@ def main():
     spec = SHAPES[name]
     rng = np.random.RandomState(0)
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    timing = os.environ.get("TC_TIMING") == "1"
+    if timing:
+        lib.demon_debug_tc_timing(1, None, 0)
     if spec[0] == "conv":
         _, B, H, W, Cin, Cout, kh, kw, sy, sx = spec
         x = torch.rand(B, H, W, Cin, device="cuda") - 0.5
@@ -50,6 +53,15 @@ def main():
             _lib.check(lib.demon_deconv4x4s2_nhwc(x.data_ptr(), out.data_ptr(), B, H, W, Cin, Cout, k.ctypes.data, b.ctypes.data, 1, prec, stream))
     torch.cuda.synchronize()
     print(name, "done; timeouts", lib.demon_debug_tc_timeouts())
+    if timing:
+        buf = np.zeros((148, 16), np.int64)
+        if lib.demon_debug_tc_timing(0, buf.ctypes.data, 148) == 0:
+            names = ["A-producer wait A_empty", "W-producer wait W_empty", "MMA wait accum_empty", "MMA wait A_full", "MMA wait A_split",
+                     "MMA wait W_full", "splitter wait A_full", "epilogue wait accum_full", "A-producer total", "MMA total", "splitter total",
+                     "epilogue total"]
+            m = buf.mean(axis=0)
+            for i, nm in enumerate(names):
+                print("  %-28s %12.0f cycles (avg per CTA)" % (nm, m[i]))
 
 
 if __name__ == "__main__":
