@@ -31,8 +31,11 @@ namespace demon {
 
 namespace {
 
-constexpr int kThreads = 352;   // 11 warps: A producer, MMA, 4 splitters, 4 epilogue, W producer
-constexpr int kMaxAStages = 3;
+constexpr int kStagerWarps = 8;
+constexpr int kWProducerWarp = 2 + kStagerWarps + 4;
+constexpr int kThreads = 32 * (kWProducerWarp + 1);   // 15 warps: A producer, MMA, 8 stagers, 4 epilogue, W producer
+constexpr int kMaxAStages = 4;
+constexpr int kMaxTStages = 8;
 constexpr int kTileH = 16, kTileW = 8;
 constexpr int kMaxPlanes = 4;
 constexpr int kMaxWStages = 8;
@@ -59,7 +62,8 @@ struct HaloParams {
   HaloPlane planes[kMaxPlanes];
   HaloTap taps[kMaxTaps];
   int a_region_bytes;   // hi image of all planes (lo image follows at the same offsets)
-  int sa;               // A stages
+  int sa;               // A (halo, shared memory) stages
+  int st;               // A-operand (TMEM) ring slots of 64 columns
   int w_stage_bytes, sw;
   int n_tile, nsplit, tmem_cols;
   const unsigned char* w;
@@ -105,32 +109,38 @@ __device__ __forceinline__ void halo_decode_tile(const HaloParams& p, int tile, 
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  // bars: A_full[3], A_split[3], A_empty[3], W_full[8], W_empty[8], accum_full[2], accum_empty[2]
-  __shared__ __align__(8) uint64_t bars[3 * kMaxAStages + 2 * kMaxWStages + 4];
+  // bars: A_full[4], A_empty[4], T_full[8], T_empty[8], W_full[8], W_empty[8], accum_full[2], accum_empty[2]
+  __shared__ __align__(8) uint64_t bars[2 * kMaxAStages + 2 * kMaxTStages + 2 * kMaxWStages + 4];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t afull0 = smem_u32(&bars[0]), asplit0 = smem_u32(&bars[kMaxAStages]), aempty0 = smem_u32(&bars[2 * kMaxAStages]);
-  const uint32_t wfull0 = smem_u32(&bars[3 * kMaxAStages]), wempty0 = smem_u32(&bars[3 * kMaxAStages + kMaxWStages]);
-  const uint32_t cfull0 = smem_u32(&bars[3 * kMaxAStages + 2 * kMaxWStages]), cempty0 = smem_u32(&bars[3 * kMaxAStages + 2 * kMaxWStages + 2]);
-  const int a_stage_bytes = 2 * p.a_region_bytes;
+  const uint32_t afull0 = smem_u32(&bars[0]), aempty0 = smem_u32(&bars[kMaxAStages]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * kMaxAStages]), tempty0 = smem_u32(&bars[2 * kMaxAStages + kMaxTStages]);
+  const uint32_t wfull0 = smem_u32(&bars[2 * kMaxAStages + 2 * kMaxTStages]);
+  const uint32_t wempty0 = smem_u32(&bars[2 * kMaxAStages + 2 * kMaxTStages + kMaxWStages]);
+  const uint32_t cfull0 = smem_u32(&bars[2 * kMaxAStages + 2 * kMaxTStages + 2 * kMaxWStages]);
+  const uint32_t cempty0 = smem_u32(&bars[2 * kMaxAStages + 2 * kMaxTStages + 2 * kMaxWStages + 2]);
+  const int a_stage_bytes = p.a_region_bytes;
   unsigned char* w_ring = smem + (size_t)p.sa * a_stage_bytes;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.nplanes; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[i]) : "memory");
     for (int s = 0; s < kMaxAStages; ++s) {
       mbar_init(afull0 + 8 * s, 1);
-      mbar_init(asplit0 + 8 * s, 4);
-      mbar_init(aempty0 + 8 * s, 1);
+      mbar_init(aempty0 + 8 * s, kStagerWarps);
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(cfull0 + 8 * s, 1);
-      mbar_init(cempty0 + 8 * s, 4);
+    for (int s = 0; s < kMaxTStages; ++s) {
+      mbar_init(tfull0 + 8 * s, 4);
+      mbar_init(tempty0 + 8 * s, 1);
     }
     for (int s = 0; s < kMaxWStages; ++s) {
       mbar_init(wfull0 + 8 * s, 1);
       mbar_init(wempty0 + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(cfull0 + 8 * s, 1);
+      mbar_init(cempty0 + 8 * s, 4);
     }
     fence_barrier_init();
   }
@@ -139,8 +149,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  const int acc_cols = p.nclass * p.n_tile;   // columns of one accumulator buffer
+  const int acc_cols = p.nclass * p.n_tile;          // columns of one accumulator buffer
+  const uint32_t t_ring = tmem_base + (uint32_t)(2 * acc_cols);   // A-operand ring: st slots of 64 columns (hi | lo)
   const bool timed = p.timing != nullptr;
+  const int steps_per_tile = p.k_chunks * p.ntaps;
 
   if (warp == 0) {
     // ===== A producer: one halo box per plane and 32-channel chunk ======================================================
@@ -167,16 +179,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
       }
       if (timed) { p.timing[blockIdx.x * 16 + 0] = w_aempty; p.timing[blockIdx.x * 16 + 8] = clock64() - t_begin; }
     }
-  } else if (warp == 10) {
-    // ===== W producer: one weight block per (chunk, tap), its own ring so that it never holds back the halo loads =======
+  } else if (warp == kWProducerWarp) {
+    // ===== W producer: one weight block per (chunk, tap), its own ring ====================================================
     if (elect_one_sync()) {
       int sw = 0;
       uint32_t pw = 0;
       long long w_wempty = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles;
-        const unsigned char* wsrc = p.w + (size_t)nt * p.k_chunks * p.ntaps * p.w_stage_bytes;
-        for (int kt = 0; kt < p.k_chunks * p.ntaps; ++kt) {
+        const unsigned char* wsrc = p.w + (size_t)nt * steps_per_tile * p.w_stage_bytes;
+        for (int kt = 0; kt < steps_per_tile; ++kt) {
           wait_t(wempty0 + 8 * sw, pw ^ 1, p.err, w_wempty, timed);
           mbar_expect_tx(wfull0 + 8 * sw, (uint32_t)p.w_stage_bytes);
           bulk_load(smem_u32(w_ring + (size_t)sw * p.w_stage_bytes), wsrc + (size_t)kt * p.w_stage_bytes, (uint32_t)p.w_stage_bytes,
@@ -187,13 +199,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
       if (timed) p.timing[blockIdx.x * 16 + 1] = w_wempty;
     }
   } else if (warp == 1) {
-    // ===== MMA issuer ====================================================================================================
+    // ===== MMA issuer: A operand from TMEM (staged by the stager warps), B operand (weights) from shared memory =========
     if (elect_one_sync()) {
-      int sa = 0, sw = 0;
-      uint32_t pa = 0, pw = 0;
+      int st = 0, sw = 0;
+      uint32_t pt = 0, pw = 0;
       const uint32_t idesc = umma_idesc_tf32(p.n_tile);
       const uint32_t w_half = (uint32_t)p.n_tile * 128u;
-      long long w_cempty = 0, w_afull = 0, w_asplit = 0, w_wfull = 0;
+      long long w_cempty = 0, w_tfull = 0, w_wfull = 0;
       const long long t_begin = clock64();
       int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -202,75 +214,100 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
         tc_fence_after();
         const uint32_t d_base = tmem_base + (uint32_t)(a * acc_cols);
         for (int kc = 0; kc < p.k_chunks; ++kc) {
-          wait_t(afull0 + 8 * sa, pa, p.err, w_afull, timed);
-          tc_fence_after();
-          bool split_ready = (p.nsplit != 3);
-          const uint32_t abase = smem_u32(smem + (size_t)sa * a_stage_bytes);
           for (int t = 0; t < p.ntaps; ++t) {
             const HaloTap& tp = p.taps[t];
-            const HaloPlane& pl = p.planes[tp.plane];
+            wait_t(tfull0 + 8 * st, pt, p.err, w_tfull, timed);
             wait_t(wfull0 + 8 * sw, pw, p.err, w_wfull, timed);
             tc_fence_after();
-            const uint32_t a_addr = abase + pl.smem_off + tp.a_off;
-            const uint32_t sbo = (uint32_t)pl.cols * 128u;
-            const uint64_t a_hi = umma_desc_sw128_sbo(a_addr, sbo), a_lo = umma_desc_sw128_sbo(a_addr + p.a_region_bytes, sbo);
+            const uint32_t a_hi = t_ring + (uint32_t)(st * 64), a_lo = a_hi + 32;
             const uint32_t wbase = smem_u32(w_ring + (size_t)sw * p.w_stage_bytes);
             const uint64_t w_hi = umma_desc_sw128_sbo(wbase, 1024), w_lo = umma_desc_sw128_sbo(wbase + w_half, 1024);
             const uint32_t d_tmem = d_base + (uint32_t)(tp.cls * p.n_tile);
             const bool fresh = (kc == 0) && tp.first;
-            // the two products on the raw halo image first; the lo image is only needed for the third
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 4; ++j) {   // 4 x K8: +8 TMEM columns / +32 bytes inside the swizzled weight row
               const uint64_t adv = (uint64_t)(2 * j);
-              if (p.nsplit == 3) umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, !(fresh && j == 0));
-              umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, (p.nsplit == 3) ? 1u : (uint32_t)!(fresh && j == 0));
-            }
-            if (p.nsplit == 3) {
-              if (!split_ready) {
-                wait_t(asplit0 + 8 * sa, pa, p.err, w_asplit, timed);
-                tc_fence_after();
-                split_ready = true;
+              if (p.nsplit == 3) {
+                umma_tf32_ts(d_tmem, a_hi + 8 * j, w_lo + adv, idesc, !(fresh && j == 0));
+                umma_tf32_ts(d_tmem, a_lo + 8 * j, w_hi + adv, idesc, 1);
+                umma_tf32_ts(d_tmem, a_hi + 8 * j, w_hi + adv, idesc, 1);
+              } else {
+                umma_tf32_ts(d_tmem, a_hi + 8 * j, w_hi + adv, idesc, !(fresh && j == 0));
               }
-#pragma unroll
-              for (int j = 0; j < 4; ++j) umma_tf32(d_tmem, a_lo + (uint64_t)(2 * j), w_hi + (uint64_t)(2 * j), idesc, 1);
             }
+            umma_commit(tempty0 + 8 * st);
             umma_commit(wempty0 + 8 * sw);
+            if (kc == p.k_chunks - 1 && t == p.ntaps - 1) umma_commit(cfull0 + 8 * a);
+            if (++st == p.st) { st = 0; pt ^= 1; }
             if (++sw == p.sw) { sw = 0; pw ^= 1; }
           }
-          umma_commit(aempty0 + 8 * sa);
-          if (kc == p.k_chunks - 1) umma_commit(cfull0 + 8 * a);
-          if (++sa == p.sa) { sa = 0; pa ^= 1; }
         }
       }
       if (timed) {
         long long* tm = p.timing + blockIdx.x * 16;
-        tm[2] = w_cempty; tm[3] = w_afull; tm[4] = w_asplit; tm[5] = w_wfull; tm[9] = clock64() - t_begin;
+        tm[2] = w_cempty; tm[3] = w_tfull; tm[5] = w_wfull; tm[9] = clock64() - t_begin;
       }
     }
-  } else if (warp < 6) {
-    // ===== splitters: lo image = A - trunc_tf32(A) over the whole halo region ===========================================
-    if (p.nsplit == 3) {
-      const int t = threadIdx.x - 64;
-      const int nvec = p.a_region_bytes >> 4;
-      int sa = 0;
-      uint32_t pa = 0;
-      long long w_safull = 0;
-      const long long t_begin = clock64();
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
-          wait_t(afull0 + 8 * sa, pa, p.err, w_safull, timed);
+  } else if (warp < 2 + kStagerWarps) {
+    // ===== stagers: halo image (shared memory) -> A operand of one tap in TMEM =========================================
+    // Thread (quadrant q, lane l) owns GEMM row m = 32q + l = tile pixel (m / 8, m % 8).  For every (chunk, tap) step it
+    // reads its (shifted) 128-byte pixel out of the swizzled halo image -- conflict free: the 8 lanes of a quarter warp
+    // hit 8 different 16-byte columns -- and writes the raw fp32 values (A_hi: the tensor core ignores the low 13
+    // mantissa bits) and A_lo = A - trunc_tf32(A) to its TMEM lane.  Two groups of four warps alternate steps.
+    const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    const int m = q * 32 + lane;
+    const int g = m >> 3, r = m & 7;
+    int sa = 0;
+    uint32_t pa = 0;
+    long long w_safull = 0, w_tempty = 0;
+    const long long t_begin = clock64();
+    int step = 0;   // global (chunk, tap) step counter of this CTA: slot = step % st
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int kc = 0; kc < p.k_chunks; ++kc) {
+        wait_t(afull0 + 8 * sa, pa, p.err, w_safull, timed);
+        __syncwarp();
+        const uint32_t abase = smem_u32(smem + (size_t)sa * a_stage_bytes);
+        for (int t = 0; t < p.ntaps; ++t, ++step) {
+          if ((step & 1) != grp) continue;
+          const int slot = step % p.st;
+          const uint32_t use = (uint32_t)(step / p.st);
+          wait_t(tempty0 + 8 * slot, (use & 1) ^ 1, p.err, w_tempty, timed);
           __syncwarp();
-          const uint32_t sb = smem_u32(smem + (size_t)sa * a_stage_bytes);
-          split_region(sb, sb + (uint32_t)p.a_region_bytes, nvec, t);
-          fence_proxy_async();
+          tc_fence_after();
+          const HaloTap& tp = p.taps[t];
+          const HaloPlane& pl = p.planes[tp.plane];
+          const uint32_t row = abase + (uint32_t)(pl.smem_off + tp.a_off + g * pl.cols * 128 + r * 128);
+          const uint32_t phase = (row >> 7) & 7u;
+          uint32_t hi[32], lo[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = lds128(row + ((c ^ phase) << 4));
+            hi[4 * c + 0] = __float_as_uint(v.x); hi[4 * c + 1] = __float_as_uint(v.y);
+            hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
+          }
+          const uint32_t taddr = t_ring + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 64);
+          tmem_st_x32(taddr, hi);
+          if (p.nsplit == 3) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) lo[c] = __float_as_uint(tf32_lo(__uint_as_float(hi[c])));
+            tmem_st_x32(taddr + 32, lo);
+          }
+          tmem_st_wait();
+          tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(asplit0 + 8 * sa);
-          if (++sa == p.sa) { sa = 0; pa ^= 1; }
+          if (lane == 0) mbar_arrive(tfull0 + 8 * slot);
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(aempty0 + 8 * sa);   // this warp is done reading the halo stage
+        if (++sa == p.sa) { sa = 0; pa ^= 1; }
       }
-      if (timed && threadIdx.x == 64) { p.timing[blockIdx.x * 16 + 6] = w_safull; p.timing[blockIdx.x * 16 + 10] = clock64() - t_begin; }
     }
-  } else if (warp < 10) {
+    if (timed && (threadIdx.x == 64 || threadIdx.x == 64 + 128)) {
+      p.timing[blockIdx.x * 16 + 6 + 6 * grp] = w_safull; p.timing[blockIdx.x * 16 + 4 + 9 * grp] = w_tempty;
+      p.timing[blockIdx.x * 16 + 10 + 4 * grp] = clock64() - t_begin;
+    }
+  } else if (warp < 2 + kStagerWarps + 4) {
     // ===== epilogue ======================================================================================================
     const int q = warp & 3;
     const int m = q * 32 + lane;
@@ -298,15 +335,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
           tmem_ld_wait();
           if (valid) {
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const int col = cbase + c0 + 4 * g;
-              if (4 * g < ncol && col < p.Cout) {
+            for (int gq = 0; gq < 8; ++gq) {
+              const int col = cbase + c0 + 4 * gq;
+              if (4 * gq < ncol && col < p.Cout) {
                 const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
                 float4 o;
-                o.x = __uint_as_float(v[4 * g + 0]) + b.x;
-                o.y = __uint_as_float(v[4 * g + 1]) + b.y;
-                o.z = __uint_as_float(v[4 * g + 2]) + b.z;
-                o.w = __uint_as_float(v[4 * g + 3]) + b.w;
+                o.x = __uint_as_float(v[4 * gq + 0]) + b.x;
+                o.y = __uint_as_float(v[4 * gq + 1]) + b.y;
+                o.z = __uint_as_float(v[4 * gq + 2]) + b.z;
+                o.w = __uint_as_float(v[4 * gq + 3]) + b.w;
                 if (p.leaky) {
                   o.x = fmaxf(0.1f * o.x, o.x); o.y = fmaxf(0.1f * o.y, o.y);
                   o.z = fmaxf(0.1f * o.z, o.z); o.w = fmaxf(0.1f * o.w, o.w);
@@ -321,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(cempty0 + 8 * a);
     }
-    if (timed && threadIdx.x == 192) { p.timing[blockIdx.x * 16 + 7] = w_cfull; p.timing[blockIdx.x * 16 + 11] = clock64() - t_begin; }
+    if (timed && q == 0 && lane == 0) { p.timing[blockIdx.x * 16 + 7] = w_cfull; p.timing[blockIdx.x * 16 + 11] = clock64() - t_begin; }
   }
 
   tc_fence_before();
@@ -393,31 +430,32 @@ static bool halo_build(const ConvProblem* probs, int nclass, int n_tile_req, int
     tp.first = (tp.cls != last_cls) ? 1 : 0;
     last_cls = tp.cls;
   }
-  // N tile: all classes accumulate side by side, double buffered, in 512 TMEM columns
+  // TMEM budget (512 columns): 2 accumulator buffers x nclass x N  +  the A-operand ring, `st` slots of 64 columns
+  // (A_hi | A_lo of one tap).  At least 4 ring slots so that the stagers run ahead of the tensor core.
   const int cout16 = (p.Cout + 15) / 16 * 16;
   int n_tile = std::min(cout16, 256);
-  const int max_n = (512 / (2 * nclass)) / 16 * 16;
+  const int max_n = ((512 - 4 * 64) / (2 * nclass)) / 16 * 16;
   n_tile = std::min(n_tile, max_n);
   if (n_tile_req > 0) n_tile = std::min(n_tile, n_tile_req);
   if (n_tile < 16) return false;
   prm.n_tile = n_tile;
   prm.n_tiles = ceil_div(p.Cout, n_tile);
+  prm.st = std::min(kMaxTStages, (512 - 2 * nclass * n_tile) / 64);
   int cols = 32;
-  while (cols < 2 * nclass * n_tile) cols <<= 1;
+  while (cols < 2 * nclass * n_tile + prm.st * 64) cols <<= 1;
   prm.tmem_cols = cols;
   prm.k_chunks = p.Cin / 32;
   // weight ring slot = one (chunk, tap) block: [W_hi | W_lo] (3xTF32) or W_hi alone, 1024-byte aligned
   const int slot = (nsplit == 3) ? n_tile * 256 : (n_tile * 128 + 1023) / 1024 * 1024;
   prm.w_stage_bytes = slot;
-  // shared memory: two A stages (a layer that cannot double-buffer its halo goes to the per-tap kernel), the rest for
-  // the weight ring
+  // shared memory: up to 4 halo stages (at least 2), the rest for the weight ring
   const int budget = 224 * 1024;
-  prm.sa = 3;
-  if (budget - prm.sa * 2 * prm.a_region_bytes < 4 * slot) prm.sa = 2;
-  const int rest = budget - prm.sa * 2 * prm.a_region_bytes;
+  prm.sa = kMaxAStages;
+  while (prm.sa > 2 && budget - prm.sa * prm.a_region_bytes < 4 * slot) --prm.sa;
+  const int rest = budget - prm.sa * prm.a_region_bytes;
   if (rest < 2 * slot) return false;
   prm.sw = std::min(kMaxWStages, rest / slot);
-  plan.smem_bytes = prm.sa * 2 * prm.a_region_bytes + prm.sw * slot + 1024;
+  plan.smem_bytes = prm.sa * prm.a_region_bytes + prm.sw * slot + 1024;
   prm.tiles_x = ceil_div(p.Wo, kTileW); prm.tiles_y = ceil_div(p.Ho, kTileH); prm.B = p.B;
   prm.total_tiles = prm.tiles_x * prm.tiles_y * p.B * prm.n_tiles;
   prm.out = p.out; prm.out_pitch = p.out_pitch; prm.Ho = p.Ho; prm.Wo = p.Wo; prm.Hfull = p.Hfull; prm.Wfull = p.Wfull;
