@@ -66,6 +66,9 @@ struct HaloParams {
   int st;               // A-operand (TMEM) ring slots of 64 columns
   int w_stage_bytes, sw;
   int n_tile, nsplit, tmem_cols;
+  int nbuf;             // accumulator buffers (2 = epilogue overlaps the next tile; 1 when TMEM is short)
+  int stacked;          // 1: 3xTF32 as two instructions on [W_hi ; W_lo] (N <= 64), 0: three instructions
+  int acc_w;            // accumulator columns per class: 2 * n_tile in 3xTF32 mode ([big | small] terms), n_tile otherwise
   const unsigned char* w;
   float* out;
   int out_pitch, Ho, Wo, Hfull, Wfull, osy, osx, Cout;
@@ -149,8 +152,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  const int acc_cols = p.nclass * p.n_tile;          // columns of one accumulator buffer
-  const uint32_t t_ring = tmem_base + (uint32_t)(2 * acc_cols);   // A-operand ring: st slots of 64 columns (hi | lo)
+  const int acc_cols = p.nclass * p.acc_w;           // columns of one accumulator buffer
+  const uint32_t t_ring = tmem_base + (uint32_t)(p.nbuf * acc_cols);   // A-operand ring: st slots of 64 columns (hi | lo)
   const bool timed = p.timing != nullptr;
   const int steps_per_tile = p.k_chunks * p.ntaps;
 
@@ -200,46 +203,69 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
     }
   } else if (warp == 1) {
     // ===== MMA issuer: A operand from TMEM (staged by the stager warps), B operand (weights) from shared memory =========
+    // This thread is the pacemaker of the whole CTA, so its per-step overhead is kept minimal: the barrier polls of step
+    // s+1 are issued BEFORE the MMAs of step s and only looked at afterwards (an mbarrier try_wait takes ~90 cycles even
+    // when the phase is already complete), and the per-tap class / first-of-class flags live in two register bitmasks.
     if (elect_one_sync()) {
       int st = 0, sw = 0;
       uint32_t pt = 0, pw = 0;
-      const uint32_t idesc = umma_idesc_tf32(p.n_tile);
-      const uint32_t w_half = (uint32_t)p.n_tile * 128u;
+      // 3xTF32 as TWO instructions per K8 step when N <= 64 ("stacked"): the weight block holds [W_hi ; W_lo] as 2N
+      // consecutive rows, so
+      //   D[:, 0:2N]  (+)= A_hi * [W_hi ; W_lo]      (one UMMA of N' = 2N: big term | first small term)
+      //   D[:, N:2N]   += A_lo * W_hi                 (second small term)
+      // and the epilogue adds the two halves: fewer, wider instructions (the tensor core has a fixed cost per
+      // instruction, tools/umma_rate_probe.cu), and the small terms accumulate apart from the big one.
+      const uint32_t idesc = umma_idesc_tf32(p.n_tile), idesc2 = umma_idesc_tf32(2 * p.n_tile);
+      uint32_t cls_bits = 0, first_bits = 0;
+      for (int t = 0; t < p.ntaps; ++t) { cls_bits |= (uint32_t)p.taps[t].cls << (2 * t); first_bits |= (uint32_t)p.taps[t].first << t; }
+      const uint32_t w_lo_off = (uint32_t)p.n_tile * 128u;
+      const uint32_t w_ring_addr = smem_u32(w_ring);
       long long w_cempty = 0, w_tfull = 0, w_wfull = 0;
       const long long t_begin = clock64();
       int it = 0;
+      bool rdy_t = mbar_try(tfull0, 0), rdy_w = mbar_try(wfull0, 0);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int a = it & 1;
-        wait_t(cempty0 + 8 * a, ((it >> 1) & 1) ^ 1, p.err, w_cempty, timed);
-        tc_fence_after();
+        const int a = (p.nbuf == 2) ? (it & 1) : 0;
+        const uint32_t cphase = (p.nbuf == 2) ? ((it >> 1) & 1) : (it & 1);
+        wait_t(cempty0 + 8 * a, cphase ^ 1, p.err, w_cempty, timed);
         const uint32_t d_base = tmem_base + (uint32_t)(a * acc_cols);
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           for (int t = 0; t < p.ntaps; ++t) {
-            const HaloTap& tp = p.taps[t];
-            wait_t(tfull0 + 8 * st, pt, p.err, w_tfull, timed);
-            wait_t(wfull0 + 8 * sw, pw, p.err, w_wfull, timed);
+            if (!rdy_t) wait_t(tfull0 + 8 * st, pt, p.err, w_tfull, timed);
+            if (!rdy_w) wait_t(wfull0 + 8 * sw, pw, p.err, w_wfull, timed);
             tc_fence_after();
             const uint32_t a_hi = t_ring + (uint32_t)(st * 64), a_lo = a_hi + 32;
-            const uint32_t wbase = smem_u32(w_ring + (size_t)sw * p.w_stage_bytes);
-            const uint64_t w_hi = umma_desc_sw128_sbo(wbase, 1024), w_lo = umma_desc_sw128_sbo(wbase + w_half, 1024);
-            const uint32_t d_tmem = d_base + (uint32_t)(tp.cls * p.n_tile);
-            const bool fresh = (kc == 0) && tp.first;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {   // 4 x K8: +8 TMEM columns / +32 bytes inside the swizzled weight row
-              const uint64_t adv = (uint64_t)(2 * j);
-              if (p.nsplit == 3) {
-                umma_tf32_ts(d_tmem, a_hi + 8 * j, w_lo + adv, idesc, !(fresh && j == 0));
-                umma_tf32_ts(d_tmem, a_lo + 8 * j, w_hi + adv, idesc, 1);
-                umma_tf32_ts(d_tmem, a_hi + 8 * j, w_hi + adv, idesc, 1);
-              } else {
-                umma_tf32_ts(d_tmem, a_hi + 8 * j, w_hi + adv, idesc, !(fresh && j == 0));
-              }
-            }
-            umma_commit(tempty0 + 8 * st);
-            umma_commit(wempty0 + 8 * sw);
-            if (kc == p.k_chunks - 1 && t == p.ntaps - 1) umma_commit(cfull0 + 8 * a);
+            const uint32_t wbase = w_ring_addr + (uint32_t)(sw * p.w_stage_bytes);
+            const int st_cur = st, sw_cur = sw;
             if (++st == p.st) { st = 0; pt ^= 1; }
             if (++sw == p.sw) { sw = 0; pw ^= 1; }
+            // poll the NEXT step's barriers now; the answers are consumed after this step's MMAs have been issued
+            rdy_t = mbar_try(tfull0 + 8 * st, pt);
+            rdy_w = mbar_try(wfull0 + 8 * sw, pw);
+            const uint64_t w_hi = umma_desc_sw128_sbo(wbase, 1024);
+            const uint32_t d_tmem = d_base + ((cls_bits >> (2 * t)) & 3u) * (uint32_t)p.acc_w;
+            const bool fresh = (kc == 0) && ((first_bits >> t) & 1u);
+            if (p.stacked) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {   // 4 x K8: +8 TMEM columns / +32 bytes inside the swizzled weight row
+                umma_tf32_ts(d_tmem, a_hi + 8 * j, w_hi + (uint64_t)(2 * j), idesc2, !(fresh && j == 0));
+                umma_tf32_ts(d_tmem + (uint32_t)p.n_tile, a_lo + 8 * j, w_hi + (uint64_t)(2 * j), idesc, 1);
+              }
+            } else if (p.nsplit == 3) {
+              const uint64_t w_lo = umma_desc_sw128_sbo(wbase + w_lo_off, 1024);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                umma_tf32_ts(d_tmem, a_hi + 8 * j, w_lo + (uint64_t)(2 * j), idesc, !(fresh && j == 0));
+                umma_tf32_ts(d_tmem, a_lo + 8 * j, w_hi + (uint64_t)(2 * j), idesc, 1);
+                umma_tf32_ts(d_tmem, a_hi + 8 * j, w_hi + (uint64_t)(2 * j), idesc, 1);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) umma_tf32_ts(d_tmem, a_hi + 8 * j, w_hi + (uint64_t)(2 * j), idesc, !(fresh && j == 0));
+            }
+            umma_commit(tempty0 + 8 * st_cur);
+            umma_commit(wempty0 + 8 * sw_cur);
+            if (kc == p.k_chunks - 1 && t == p.ntaps - 1) umma_commit(cfull0 + 8 * a);
           }
         }
       }
@@ -262,17 +288,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
     uint32_t pa = 0;
     long long w_safull = 0, w_tempty = 0;
     const long long t_begin = clock64();
-    int step = 0;   // global (chunk, tap) step counter of this CTA: slot = step % st
+    int step = 0;    // global (chunk, tap) step counter of this CTA
+    int slot = 0;    // = step % st, kept incrementally (no division in the loop)
+    uint32_t use = 0;   // parity of step / st
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       for (int kc = 0; kc < p.k_chunks; ++kc) {
         wait_t(afull0 + 8 * sa, pa, p.err, w_safull, timed);
         __syncwarp();
         const uint32_t abase = smem_u32(smem + (size_t)sa * a_stage_bytes);
         for (int t = 0; t < p.ntaps; ++t, ++step) {
+          const int slot_cur = slot;
+          const uint32_t use_cur = use;
+          if (++slot == p.st) { slot = 0; use ^= 1; }
           if ((step & 1) != grp) continue;
-          const int slot = step % p.st;
-          const uint32_t use = (uint32_t)(step / p.st);
-          wait_t(tempty0 + 8 * slot, (use & 1) ^ 1, p.err, w_tempty, timed);
+          wait_t(tempty0 + 8 * slot_cur, use_cur ^ 1, p.err, w_tempty, timed);
           __syncwarp();
           tc_fence_after();
           const HaloTap& tp = p.taps[t];
@@ -286,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
             hi[4 * c + 0] = __float_as_uint(v.x); hi[4 * c + 1] = __float_as_uint(v.y);
             hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
           }
-          const uint32_t taddr = t_ring + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 64);
+          const uint32_t taddr = t_ring + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot_cur * 64);
           tmem_st_x32(taddr, hi);
           if (p.nsplit == 3) {
 #pragma unroll
@@ -296,7 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tfull0 + 8 * slot);
+          if (lane == 0) mbar_arrive(tfull0 + 8 * slot_cur);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(aempty0 + 8 * sa);   // this warp is done reading the halo stage
@@ -304,8 +333,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
       }
     }
     if (timed && (threadIdx.x == 64 || threadIdx.x == 64 + 128)) {
-      p.timing[blockIdx.x * 16 + 6 + 6 * grp] = w_safull; p.timing[blockIdx.x * 16 + 4 + 9 * grp] = w_tempty;
-      p.timing[blockIdx.x * 16 + 10 + 4 * grp] = clock64() - t_begin;
+      if (grp == 0) { p.timing[blockIdx.x * 16 + 6] = w_safull; p.timing[blockIdx.x * 16 + 4] = w_tempty; p.timing[blockIdx.x * 16 + 10] = clock64() - t_begin; }
+      else p.timing[blockIdx.x * 16 + 12] = w_tempty;
     }
   } else if (warp < 2 + kStagerWarps + 4) {
     // ===== epilogue ======================================================================================================
@@ -318,8 +347,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       int nt, n, y0, x0;
       halo_decode_tile(p, tile, nt, n, y0, x0);
-      const int a = it & 1;
-      wait_t(cfull0 + 8 * a, (it >> 1) & 1, p.err, w_cfull, timed);
+      const int a = (p.nbuf == 2) ? (it & 1) : 0;
+      wait_t(cfull0 + 8 * a, (p.nbuf == 2) ? ((it >> 1) & 1) : (it & 1), p.err, w_cfull, timed);
       __syncwarp();
       tc_fence_after();
       const int oy = y0 + yl, ox = x0 + xl;
@@ -327,11 +356,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
       const int cbase = nt * p.n_tile;
       for (int cls = 0; cls < p.nclass; ++cls) {
         float* orow = p.out + ((size_t)(n * p.Hfull + oy * p.osy + p.cls_ooy[cls]) * p.Wfull + ox * p.osx + p.cls_oox[cls]) * p.out_pitch;
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * acc_cols + cls * p.n_tile);
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * acc_cols + cls * p.acc_w);
         for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
           uint32_t v[32];
           const int ncol = (p.n_tile - c0) >= 32 ? 32 : 16;
           if (ncol == 32) tmem_ld_x32(t_row + c0, v); else tmem_ld_x16(t_row + c0, v);
+          if (p.stacked) {   // big term + small terms
+            uint32_t u[32];
+            if (ncol == 32) tmem_ld_x32(t_row + p.n_tile + c0, u); else tmem_ld_x16(t_row + p.n_tile + c0, u);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
+          }
           tmem_ld_wait();
           if (valid) {
 #pragma unroll
@@ -430,19 +466,28 @@ static bool halo_build(const ConvProblem* probs, int nclass, int n_tile_req, int
     tp.first = (tp.cls != last_cls) ? 1 : 0;
     last_cls = tp.cls;
   }
-  // TMEM budget (512 columns): 2 accumulator buffers x nclass x N  +  the A-operand ring, `st` slots of 64 columns
-  // (A_hi | A_lo of one tap).  At least 4 ring slots so that the stagers run ahead of the tensor core.
+  // TMEM budget (512 columns): nbuf accumulator buffers x nclass x acc_w  +  the A-operand ring, `st` slots of 64
+  // columns (A_hi | A_lo of one tap), at least 4 slots so that the stagers run ahead of the tensor core.
+  // acc_w = 2N in 3xTF32 mode (big | small terms side by side, see the MMA role), N otherwise.
   const int cout16 = (p.Cout + 15) / 16 * 16;
-  int n_tile = std::min(cout16, 256);
-  const int max_n = ((512 - 4 * 64) / (2 * nclass)) / 16 * 16;
+  prm.stacked = (nsplit == 3 && cout16 <= 64) ? 1 : 0;
+  const int wmul = prm.stacked ? 2 : 1;
+  int n_tile = std::min(cout16, 256 / wmul);
+  prm.nbuf = 2;
+  int max_n = ((512 - 4 * 64) / (prm.nbuf * nclass * wmul)) / 16 * 16;
+  if (max_n < std::min(cout16, 32)) {   // e.g. the 4 sub-pixel classes: single-buffer the accumulators instead of splitting N
+    prm.nbuf = 1;
+    max_n = ((512 - 4 * 64) / (nclass * wmul)) / 16 * 16;
+  }
   n_tile = std::min(n_tile, max_n);
   if (n_tile_req > 0) n_tile = std::min(n_tile, n_tile_req);
   if (n_tile < 16) return false;
   prm.n_tile = n_tile;
+  prm.acc_w = wmul * n_tile;
   prm.n_tiles = ceil_div(p.Cout, n_tile);
-  prm.st = std::min(kMaxTStages, (512 - 2 * nclass * n_tile) / 64);
+  prm.st = std::min(kMaxTStages, (512 - prm.nbuf * nclass * prm.acc_w) / 64);
   int cols = 32;
-  while (cols < 2 * nclass * n_tile + prm.st * 64) cols <<= 1;
+  while (cols < prm.nbuf * nclass * prm.acc_w + prm.st * 64) cols <<= 1;
   prm.tmem_cols = cols;
   prm.k_chunks = p.Cin / 32;
   // weight ring slot = one (chunk, tap) block: [W_hi | W_lo] (3xTF32) or W_hi alone, 1024-byte aligned

@@ -33,6 +33,18 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
+// non-blocking probe (try_wait may suspend the thread for a hardware time-out when the phase is still pending)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, int* err) {
   const long long t0 = clock64();
   for (;;) {
