@@ -59,6 +59,10 @@ struct HaloTap {
 struct HaloParams {
   int tiles_x, tiles_y, B, n_tiles, total_tiles;
   int k_chunks, nplanes, ntaps, nclass;
+  // per-tap mode (layers whose images are not made of whole 16x8 tiles): the A stage is ONE tap's 128-pixel tile
+  // (tb images x th rows x tw columns, one TMA box per (chunk, tap) step, box coordinates carry the tap like in conv_tc.cu)
+  int per_tap, tw, th, tb, tiles_b, aempty_count;
+  int tap_c[kMaxTaps], tap_qx[kMaxTaps], tap_ry[kMaxTaps], tap_qy[kMaxTaps];
   HaloPlane planes[kMaxPlanes];
   HaloTap taps[kMaxTaps];
   int a_region_bytes;   // hi image of all planes (lo image follows at the same offsets)
@@ -99,6 +103,7 @@ __device__ __forceinline__ void wait_t(uint32_t bar, uint32_t parity, int* err, 
   acc += clock64() - t0;
 }
 
+template <bool PER_TAP>
 __device__ __forceinline__ void halo_decode_tile(const HaloParams& p, int tile, int& nt, int& n, int& y0, int& x0) {
   nt = tile % p.n_tiles;
   int m = tile / p.n_tiles;
@@ -106,9 +111,11 @@ __device__ __forceinline__ void halo_decode_tile(const HaloParams& p, int tile, 
   m /= p.tiles_x;
   const int yb = m % p.tiles_y;
   n = m / p.tiles_y;
-  y0 = yb * kTileH; x0 = xb * kTileW;
+  if (PER_TAP) { n *= p.tb; y0 = yb * p.th; x0 = xb * p.tw; }
+  else { y0 = yb * kTileH; x0 = xb * kTileW; }
 }
 
+template <bool PER_TAP>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -131,7 +138,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
     for (int i = 0; i < p.nplanes; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[i]) : "memory");
     for (int s = 0; s < kMaxAStages; ++s) {
       mbar_init(afull0 + 8 * s, 1);
-      mbar_init(aempty0 + 8 * s, kStagerWarps);
+      mbar_init(aempty0 + 8 * s, (uint32_t)p.aempty_count);
     }
     for (int s = 0; s < kMaxTStages; ++s) {
       mbar_init(tfull0 + 8 * s, 4);
@@ -168,8 +175,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
       for (int i = 0; i < p.nplanes; ++i) a_bytes += (uint32_t)p.planes[i].bytes;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int nt, n, y0, x0;
-        halo_decode_tile(p, tile, nt, n, y0, x0);
+        halo_decode_tile<PER_TAP>(p, tile, nt, n, y0, x0);
         for (int kc = 0; kc < p.k_chunks; ++kc) {
+          if (PER_TAP) {
+            for (int t = 0; t < p.ntaps; ++t) {
+              wait_t(aempty0 + 8 * sa, pa ^ 1, p.err, w_aempty, timed);
+              mbar_expect_tx(afull0 + 8 * sa, 128u * 128u);
+              tma_load_5d(smem_u32(smem + (size_t)sa * a_stage_bytes), &maps.m[0], afull0 + 8 * sa, p.tap_c[t] + kc * 32, x0 + p.tap_qx[t],
+                          p.tap_ry[t], y0 + p.tap_qy[t], n);
+              if (++sa == p.sa) { sa = 0; pa ^= 1; }
+            }
+            continue;
+          }
           wait_t(aempty0 + 8 * sa, pa ^ 1, p.err, w_aempty, timed);
           const uint32_t abase = smem_u32(smem + (size_t)sa * a_stage_bytes);
           mbar_expect_tx(afull0 + 8 * sa, a_bytes);
@@ -293,20 +310,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
     uint32_t use = 0;   // parity of step / st
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       for (int kc = 0; kc < p.k_chunks; ++kc) {
-        wait_t(afull0 + 8 * sa, pa, p.err, w_safull, timed);
-        __syncwarp();
-        const uint32_t abase = smem_u32(smem + (size_t)sa * a_stage_bytes);
+        uint32_t abase = 0;
+        if (!PER_TAP) {
+          wait_t(afull0 + 8 * sa, pa, p.err, w_safull, timed);
+          __syncwarp();
+          abase = smem_u32(smem + (size_t)sa * a_stage_bytes);
+        }
         for (int t = 0; t < p.ntaps; ++t, ++step) {
           const int slot_cur = slot;
           const uint32_t use_cur = use;
           if (++slot == p.st) { slot = 0; use ^= 1; }
+          const int sa_cur = sa;
+          const uint32_t pa_cur = pa;
+          if (PER_TAP) { if (++sa == p.sa) { sa = 0; pa ^= 1; } }   // one A stage per step
           if ((step & 1) != grp) continue;
+          uint32_t row;
+          if (PER_TAP) {
+            wait_t(afull0 + 8 * sa_cur, pa_cur, p.err, w_safull, timed);
+            __syncwarp();
+            row = smem_u32(smem + (size_t)sa_cur * a_stage_bytes) + (uint32_t)(g * 1024 + r * 128);
+          } else {
+            const HaloTap& tp = p.taps[t];
+            const HaloPlane& pl = p.planes[tp.plane];
+            row = abase + (uint32_t)(pl.smem_off + tp.a_off + g * pl.cols * 128 + r * 128);
+          }
           wait_t(tempty0 + 8 * slot_cur, use_cur ^ 1, p.err, w_tempty, timed);
           __syncwarp();
           tc_fence_after();
-          const HaloTap& tp = p.taps[t];
-          const HaloPlane& pl = p.planes[tp.plane];
-          const uint32_t row = abase + (uint32_t)(pl.smem_off + tp.a_off + g * pl.cols * 128 + r * 128);
           const uint32_t phase = (row >> 7) & 7u;
           uint32_t hi[32], lo[32];
 #pragma unroll
@@ -325,11 +355,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tfull0 + 8 * slot_cur);
+          if (lane == 0) {
+            mbar_arrive(tfull0 + 8 * slot_cur);
+            if (PER_TAP) mbar_arrive(aempty0 + 8 * sa_cur);   // the tap's tile has been consumed: stage back to the producer
+          }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(aempty0 + 8 * sa);   // this warp is done reading the halo stage
-        if (++sa == p.sa) { sa = 0; pa ^= 1; }
+        if (!PER_TAP) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(aempty0 + 8 * sa);   // this warp is done reading the halo stage
+          if (++sa == p.sa) { sa = 0; pa ^= 1; }
+        }
       }
     }
     if (timed && (threadIdx.x == 64 || threadIdx.x == 64 + 128)) {
@@ -340,19 +375,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
     // ===== epilogue ======================================================================================================
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    const int yl = m >> 3, xl = m & 7;
+    const int xl = PER_TAP ? (m % p.tw) : (m & 7);
+    const int yl = PER_TAP ? ((m / p.tw) % p.th) : (m >> 3);
+    const int nl = PER_TAP ? (m / (p.tw * p.th)) : 0;
     long long w_cfull = 0;
     const long long t_begin = clock64();
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       int nt, n, y0, x0;
-      halo_decode_tile(p, tile, nt, n, y0, x0);
+      halo_decode_tile<PER_TAP>(p, tile, nt, n, y0, x0);
       const int a = (p.nbuf == 2) ? (it & 1) : 0;
       wait_t(cfull0 + 8 * a, (p.nbuf == 2) ? ((it >> 1) & 1) : (it & 1), p.err, w_cfull, timed);
       __syncwarp();
       tc_fence_after();
       const int oy = y0 + yl, ox = x0 + xl;
-      const bool valid = oy < p.Ho && ox < p.Wo;
+      n += nl;
+      const bool valid = oy < p.Ho && ox < p.Wo && n < p.B;
       const int cbase = nt * p.n_tile;
       for (int cls = 0; cls < p.nclass; ++cls) {
         float* orow = p.out + ((size_t)(n * p.Hfull + oy * p.osy + p.cls_ooy[cls]) * p.Wfull + ox * p.osx + p.cls_oox[cls]) * p.out_pitch;
@@ -416,12 +454,46 @@ struct HaloPlan {
   int smem_bytes;
 };
 
+static int pow2_ceil_h(int v) { int r = 1; while (r < v) r <<= 1; return r; }
+
 static bool halo_build(const ConvProblem* probs, int nclass, int n_tile_req, int nsplit, HaloPlan& plan, bool encode) {
   const ConvProblem& p = probs[0];
   HaloParams& prm = plan.prm;
   memset(&prm, 0, sizeof(prm));
   prm.nclass = nclass;
   prm.nsplit = nsplit;
+  prm.per_tap = ((p.Ho % kTileH) != 0 || (p.Wo % kTileW) != 0) ? 1 : 0;
+  int m_tiles = 0;
+  if (prm.per_tap) {
+    // one 128-pixel tile per (chunk, tap) step, tb images x th rows x tw columns (same tiling rule as conv_tc.cu)
+    int ntaps = 0;
+    for (int c = 0; c < nclass; ++c)
+      for (int i = 0; i < probs[c].ntaps; ++i, ++ntaps) {
+        if (ntaps >= kMaxTaps) return false;
+        const int qy = floor_div_h(probs[c].dy[i], p.sy), qx = floor_div_h(probs[c].dx[i], p.sx);
+        prm.tap_qy[ntaps] = qy; prm.tap_ry[ntaps] = probs[c].dy[i] - qy * p.sy;
+        prm.tap_qx[ntaps] = qx; prm.tap_c[ntaps] = (probs[c].dx[i] - qx * p.sx) * p.in_pitch;
+        prm.taps[ntaps].plane = 0; prm.taps[ntaps].a_off = 0; prm.taps[ntaps].cls = c; prm.taps[ntaps].first = (i == 0) ? 1 : 0;
+      }
+    prm.ntaps = ntaps;
+    prm.nplanes = 1;
+    long best_tiles = -1;
+    const int tw = std::min(128, pow2_ceil_h(p.Wo));
+    for (int th = 1; th * tw <= 128; th <<= 1) {
+      const int tb = 128 / (tw * th);
+      const long tiles = (long)ceil_div(p.Wo, tw) * ceil_div(p.Ho, th) * ceil_div(p.B, tb);
+      if (best_tiles < 0 || tiles <= best_tiles) {
+        best_tiles = tiles;
+        prm.tw = tw; prm.th = th; prm.tb = tb;
+        prm.tiles_x = ceil_div(p.Wo, tw); prm.tiles_y = ceil_div(p.Ho, th); prm.tiles_b = ceil_div(p.B, tb);
+      }
+    }
+    prm.planes[0].cols = prm.tw; prm.planes[0].rows = prm.th; prm.planes[0].bytes = 128 * 128;
+    prm.a_region_bytes = 128 * 128;
+    prm.aempty_count = 4;     // the four stager warps of the group that consumed the tap release its shared-memory stage
+    m_tiles = prm.tiles_x * prm.tiles_y * prm.tiles_b;
+  } else {
+  prm.aempty_count = kStagerWarps;
   // planes: taps grouped by stride parity
   struct PInfo { int ry, rx, qy_min, qy_max, qx_min, qx_max; };
   std::vector<PInfo> pinfo;
@@ -466,24 +538,30 @@ static bool halo_build(const ConvProblem* probs, int nclass, int n_tile_req, int
     tp.first = (tp.cls != last_cls) ? 1 : 0;
     last_cls = tp.cls;
   }
+  prm.tiles_x = ceil_div(p.Wo, kTileW); prm.tiles_y = ceil_div(p.Ho, kTileH); prm.tiles_b = p.B;
+  m_tiles = prm.tiles_x * prm.tiles_y * p.B;
+  }
   // TMEM budget (512 columns): nbuf accumulator buffers x nclass x acc_w  +  the A-operand ring, `st` slots of 64
   // columns (A_hi | A_lo of one tap), at least 4 slots so that the stagers run ahead of the tensor core.
-  // acc_w = 2N in 3xTF32 mode (big | small terms side by side, see the MMA role), N otherwise.
+  // acc_w = 2N in stacked 3xTF32 mode (big | small terms side by side, see the MMA role), N otherwise.
   const int cout16 = (p.Cout + 15) / 16 * 16;
-  prm.stacked = (nsplit == 3 && cout16 <= 64) ? 1 : 0;
-  const int wmul = prm.stacked ? 2 : 1;
-  int n_tile = std::min(cout16, 256 / wmul);
-  prm.nbuf = 2;
-  int max_n = ((512 - 4 * 64) / (prm.nbuf * nclass * wmul)) / 16 * 16;
-  if (max_n < std::min(cout16, 32)) {   // e.g. the 4 sub-pixel classes: single-buffer the accumulators instead of splitting N
-    prm.nbuf = 1;
-    max_n = ((512 - 4 * 64) / (nclass * wmul)) / 16 * 16;
-  }
-  n_tile = std::min(n_tile, max_n);
+  auto fits = [&](int n, int wm, int& nbuf_out) {
+    for (int nb = 2; nb >= 1; --nb)
+      if (nb * nclass * wm * n + 4 * 64 <= 512) { nbuf_out = nb; return true; }
+    return false;
+  };
+  int n_tile = std::min(cout16, 256), nbuf = 2;
+  while (n_tile >= 16 && !fits(n_tile, 1, nbuf)) n_tile = (n_tile > 32) ? (n_tile / 2 + 15) / 16 * 16 : n_tile - 16;
   if (n_tile_req > 0) n_tile = std::min(n_tile, n_tile_req);
-  if (n_tile < 16) return false;
+  // narrow the N tile (down to 64) while the layer would leave SMs idle
+  while (n_tile >= 128 && (n_tile % 32) == 0 && (long)m_tiles * ceil_div(p.Cout, n_tile) < 148) n_tile /= 2;
+  if (n_tile < 16 || !fits(n_tile, 1, nbuf)) return false;
+  prm.stacked = 0;
+  int nbuf2 = 0;
+  if (nsplit == 3 && n_tile <= 64 && fits(n_tile, 2, nbuf2)) { prm.stacked = 1; nbuf = nbuf2; }
+  prm.nbuf = nbuf;
   prm.n_tile = n_tile;
-  prm.acc_w = wmul * n_tile;
+  prm.acc_w = (prm.stacked ? 2 : 1) * n_tile;
   prm.n_tiles = ceil_div(p.Cout, n_tile);
   prm.st = std::min(kMaxTStages, (512 - prm.nbuf * nclass * prm.acc_w) / 64);
   int cols = 32;
@@ -501,8 +579,8 @@ static bool halo_build(const ConvProblem* probs, int nclass, int n_tile_req, int
   if (rest < 2 * slot) return false;
   prm.sw = std::min(kMaxWStages, rest / slot);
   plan.smem_bytes = prm.sa * prm.a_region_bytes + prm.sw * slot + 1024;
-  prm.tiles_x = ceil_div(p.Wo, kTileW); prm.tiles_y = ceil_div(p.Ho, kTileH); prm.B = p.B;
-  prm.total_tiles = prm.tiles_x * prm.tiles_y * p.B * prm.n_tiles;
+  prm.B = p.B;
+  prm.total_tiles = m_tiles * prm.n_tiles;
   prm.out = p.out; prm.out_pitch = p.out_pitch; prm.Ho = p.Ho; prm.Wo = p.Wo; prm.Hfull = p.Hfull; prm.Wfull = p.Wfull;
   prm.osy = p.osy; prm.osx = p.osx; prm.Cout = p.Cout; prm.bias = p.bias; prm.leaky = p.leaky;
   for (int c = 0; c < nclass; ++c) { prm.cls_ooy[c] = probs[c].ooy; prm.cls_oox[c] = probs[c].oox; }
@@ -523,7 +601,7 @@ static bool halo_build(const ConvProblem* probs, int nclass, int n_tile_req, int
                         (cuuint64_t)p.Hi * p.Wi * cp * 4};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   for (int i = 0; i < prm.nplanes; ++i) {
-    cuuint32_t box[5] = {32, (cuuint32_t)prm.planes[i].cols, 1, (cuuint32_t)prm.planes[i].rows, 1};
+    cuuint32_t box[5] = {32, (cuuint32_t)prm.planes[i].cols, 1, (cuuint32_t)prm.planes[i].rows, (cuuint32_t)(prm.per_tap ? prm.tb : 1)};
     CUresult r = enc(&plan.maps.m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(p.in), gdim, gstr, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -537,7 +615,9 @@ bool tc_halo_supported(const ConvProblem* probs, int nclass) {
   const ConvProblem& p = probs[0];
   for (int c = 0; c < nclass; ++c)
     if (!tc_layer_supported(probs[c])) return false;
-  if ((p.Ho % kTileH) != 0 || (p.Wo % kTileW) != 0) return false;   // whole tiles only; other layers use the per-tap kernel
+  // per-tap TS mode pays off for plain convolutions at low resolution; the 4-class transposed convolutions there are
+  // TMEM-limited (single accumulator buffer, split N) and stay on the shared-memory-operand kernel (conv_tc.cu)
+  if (((p.Ho % kTileH) != 0 || (p.Wo % kTileW) != 0) && nclass != 1) return false;
   HaloPlan plan;
   return halo_build(probs, nclass, 0, 3, plan, false);
 }
@@ -630,7 +710,8 @@ int conv_tc_halo_launch(const TcLayer& t, const ConvProblem* probs, cudaStream_t
   prm.timing = g_timing_dev;
   static bool attr_set = false;
   if (!attr_set) {
-    DEMON_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    DEMON_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    DEMON_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr_set = true;
   }
   int sms = 0, dev = 0;
@@ -638,7 +719,8 @@ int conv_tc_halo_launch(const TcLayer& t, const ConvProblem* probs, cudaStream_t
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (sms <= 0) sms = 148;
   const int grid = std::min(prm.total_tiles, sms);
-  conv_tc_halo_kernel<<<grid, kThreads, plan->smem_bytes, stream>>>(plan->maps, prm);
+  if (prm.per_tap) conv_tc_halo_kernel<true><<<grid, kThreads, plan->smem_bytes, stream>>>(plan->maps, prm);
+  else conv_tc_halo_kernel<false><<<grid, kThreads, plan->smem_bytes, stream>>>(plan->maps, prm);
   DEMON_LAUNCH_CHECK();
   return DEMON_OK;
 }
