@@ -258,7 +258,11 @@ def main():
 
     # ---- per-layer device time -> roofline of the dominant kernel ------------------------------------
     lm = W.layer_macs()
-    fam = {"tc": [0.0, 0.0, 0], "simt": [0.0, 0.0, 0]}   # ms, MACs, launches
+    FAMILIES = {0: "conv_simt_kernel (fp32 CUDA-core implicit GEMM)",
+                1: "conv_tc_kernel (tcgen05 kind::tf32, operands in shared memory, %s)" % precision,
+                2: "conv_tc_halo_kernel<false> (tcgen05 kind::tf32, TMA halo tile, A operand in TMEM, %s)" % precision,
+                3: "conv_tc_halo_kernel<true> (tcgen05 kind::tf32, per-tap tiles, A operand in TMEM, %s)" % precision}
+    fam = {k: [0.0, 0.0, 0] for k in FAMILIES}   # ms, MACs, launches
     top = []
     for i in range(lib.demon_net_num_layers(net.ptr)):
         name = lib.demon_net_layer_name(net.ptr, i).decode()
@@ -267,29 +271,42 @@ def main():
         if calls.value == 0:
             continue
         macs = lm[name] * B * calls.value
-        f = fam["tc" if tc.value else "simt"]
+        f = fam[tc.value]
         f[0] += t.value; f[1] += macs; f[2] += calls.value * lpc.value
-        top.append((t.value, name, macs, bool(tc.value)))
+        top.append((t.value, name, macs, tc.value))
     top.sort(reverse=True)
     pk = peaks()
-    dom = "tc" if fam["tc"][0] > 0 else "simt"
+    dom = max(fam, key=lambda k: fam[k][0])
     d_ms, d_macs, d_launches = fam[dom]
     achieved = 2.0 * d_macs / (d_ms / 1e3) / 1e12 if d_ms > 0 else 0.0
-    if dom == "tc":
+    if dom != 0:
         peak = pk["bf16_tflops_sustained"] / 2.0
-        peak_note = "%s bf16 sustained %.1f TF/s / 2 (kind::tf32 issues at half the bf16 rate); %s issues %d MMAs per algorithmic MAC" % (
-            pk["source"], pk["bf16_tflops_sustained"], precision, 3 if precision == "3xtf32" else 1)
-        kernel = "conv_tc_kernel (tcgen05 kind::tf32 implicit GEMM, %s)" % precision
+        peak_note = ("%s bf16 sustained %.1f TF/s / 2 (kind::tf32 issues at half the bf16 rate); %s spends %d tensor MACs per "
+                     "algorithmic MAC, so frac <= %.2f by construction" % (pk["source"], pk["bf16_tflops_sustained"], precision,
+                                                                          3 if precision == "3xtf32" else 1, 1 / 3 if precision == "3xtf32" else 1))
     else:
         peak = 2 * 128 * 148 * 1.965e9 / 1e12     # fp32 FFMA peak at clocks.max.sm
         peak_note = "fp32 FFMA peak 128 FMA/clk/SM x 148 SMs x 1965 MHz (no measured fp32 figure in MEASURED_PEAKS.json)"
-        kernel = "conv_simt_kernel (fp32 CUDA-core implicit GEMM)"
-    roofline = {"bound": "tensor", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak if peak else None, "traffic": None,
+    # DRAM traffic of the heaviest launch of the dominant kernel, from the committed `ncu --set full` capture (profiles/)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.isfile(tpath):
+        tj = json.load(open(tpath))
+        key = {2: "refine0_upconv", 1: "refine2_upconv", 3: "conv3x"}.get(dom)
+        if key in tj:
+            traffic = {"bytes": tj[key], "launch": key, "algorithmic_bytes": {"refine0_upconv": 2 * 64 * 96 * 128 * 128 * 4 + 4 * 4 * 128 * 32 * 4,
+                                                                              "refine2_upconv": 64 * 24 * 32 * 256 * 4 + 64 * 48 * 64 * 64 * 4,
+                                                                              "conv3x": 64 * 24 * 64 * 128 * 4 + 64 * 24 * 32 * 128 * 4}.get(key),
+                       "source": "profiles/r01_ncu_full.md (one launch at batch 64, dram__bytes_read.sum + dram__bytes_write.sum)"}
+    roofline = {"bound": "tensor", "kernel": FAMILIES[dom], "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak if peak else None, "traffic": traffic,
                 "algorithmic_flops_per_launch": 2.0 * d_macs / max(1, d_launches), "avg_launch_ms": d_ms / max(1, d_launches),
                 "launches_timed": d_launches, "kernel_share_of_step": d_ms / ms_local if ms_local else None, "peak_note": peak_note,
-                "top_layers_ms_per_step": [{"layer": n, "ms": t / args.steps, "tflops": 2.0 * m / (t / 1e3) / 1e12 if t > 0 else 0, "tc": tc}
-                                           for t, n, m, tc in top[:8]]}
+                "kernels": [{"kernel": FAMILIES[k], "ms_per_step": fam[k][0] / args.steps, "share_of_step": fam[k][0] / ms_local,
+                             "tflops": 2.0 * fam[k][1] / (fam[k][0] / 1e3) / 1e12 if fam[k][0] > 0 else 0, "launches_per_step": fam[k][2] // args.steps}
+                            for k in sorted(fam, key=lambda k: -fam[k][0]) if fam[k][2]],
+                "top_layers_ms_per_step": [{"layer": n, "ms": t / args.steps, "tflops": 2.0 * m / (t / 1e3) / 1e12 if t > 0 else 0, "kernel": k}
+                                           for t, n, m, k in top[:8]]}
 
     # ---- end to end through the C-ABI host entry (pinned host buffers, copies inside the timed region) ----
     e2e = None

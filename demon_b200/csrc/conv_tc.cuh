@@ -18,6 +18,7 @@ struct TcLayer {
   int stages = 0;
   int smem_bytes = 0;
   unsigned char tmap_host[128];
+  int per_tap = 0;            // halo kernel in per-tap mode (low-resolution layers)
   void* halo_plan = nullptr;  // non-null: the layer runs on the halo kernel (conv_tc_halo.cu); owned
 };
 

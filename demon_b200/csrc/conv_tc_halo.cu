@@ -676,6 +676,7 @@ int tc_halo_prepare(TcLayer& t, const ConvProblem* probs, const float* const* w_
   plan->prm.w = static_cast<const unsigned char*>(dw);
   t.w_packed = dw;
   t.halo_plan = plan;
+  t.per_tap = prm.per_tap;
   t.nclass = nclass;
   t.n_tile = prm.n_tile; t.n_tiles = prm.n_tiles; t.k_chunks = prm.k_chunks; t.nsplit = nsplit;
   t.th = kTileH; t.tw = kTileW; t.tb = 1; t.stages = prm.sa; t.smem_bytes = plan->smem_bytes;

@@ -821,7 +821,8 @@ int demon_net_layer_profile(const demon_net* n, int i, double* ms, int64_t* call
   if (ms) *ms = i < (int)n->prof_ms.size() ? n->prof_ms[i] : 0.0;
   if (calls) *calls = i < (int)n->prof_calls.size() ? n->prof_calls[i] : 0;
   if (launches_per_call) *launches_per_call = n->layers[i]->use_tc ? 1 : (n->layers[i]->kind == L_DECONV ? 4 : (n->layers[i]->ksplit > 1 ? 2 : 1));
-  if (uses_tc) *uses_tc = n->layers[i]->use_tc ? 1 : 0;
+  // kernel family: 0 conv_simt_kernel, 1 conv_tc_kernel, 2 conv_tc_halo_kernel<false> (halo), 3 conv_tc_halo_kernel<true> (per tap)
+  if (uses_tc) *uses_tc = !n->layers[i]->use_tc ? 0 : (!n->layers[i]->tc.halo_plan ? 1 : (n->layers[i]->tc.per_tap ? 3 : 2));
   return DEMON_OK;
 }
 

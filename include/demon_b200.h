@@ -175,6 +175,8 @@ int demon_net_profile_begin(demon_net* net);
 int demon_net_profile_end(demon_net* net);
 int demon_net_num_layers(const demon_net* net);
 const char* demon_net_layer_name(const demon_net* net, int i);
+/* uses_tc: kernel family of the layer -- 0 conv_simt_kernel (fp32 CUDA cores), 1 conv_tc_kernel (tcgen05, operands in
+ * shared memory), 2 conv_tc_halo_kernel<false> (tcgen05, halo tile, A operand in TMEM), 3 conv_tc_halo_kernel<true> (per tap) */
 int demon_net_layer_profile(const demon_net* net, int i, double* ms, int64_t* calls, int* launches_per_call,
                             int* uses_tc);
 
