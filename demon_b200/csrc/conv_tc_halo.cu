@@ -63,6 +63,11 @@ struct HaloParams {
   // (tb images x th rows x tw columns, one TMA box per (chunk, tap) step, box coordinates carry the tap like in conv_tc.cu)
   int per_tap, tw, th, tb, tiles_b, aempty_count;
   int tap_c[kMaxTaps], tap_qx[kMaxTaps], tap_ry[kMaxTaps], tap_qy[kMaxTaps];
+  // 8-channel mode (Cin == 8, e.g. the image pair): a pixel is 32 bytes in shared memory (no swizzle), the halo is loaded
+  // once per tile, and one K = 32 step gathers FOUR taps x 8 channels into the TMEM A operand (`ntaps` then counts these
+  // groups, g_plane / g_aoff describe the real taps, -1 = missing tap -> zero columns)
+  int cin8, ntaps_real;
+  int g_plane[kMaxTaps], g_aoff[kMaxTaps];
   HaloPlane planes[kMaxPlanes];
   HaloTap taps[kMaxTaps];
   int a_region_bytes;   // hi image of all planes (lo image follows at the same offsets)
@@ -115,7 +120,7 @@ __device__ __forceinline__ void halo_decode_tile(const HaloParams& p, int tile, 
   else { y0 = yb * kTileH; x0 = xb * kTileW; }
 }
 
-template <bool PER_TAP>
+template <bool PER_TAP, bool CIN8>
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -329,21 +334,42 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
             wait_t(afull0 + 8 * sa_cur, pa_cur, p.err, w_safull, timed);
             __syncwarp();
             row = smem_u32(smem + (size_t)sa_cur * a_stage_bytes) + (uint32_t)(g * 1024 + r * 128);
-          } else {
+          } else if (!CIN8) {
             const HaloTap& tp = p.taps[t];
             const HaloPlane& pl = p.planes[tp.plane];
             row = abase + (uint32_t)(pl.smem_off + tp.a_off + g * pl.cols * 128 + r * 128);
+          } else {
+            row = 0;
           }
           wait_t(tempty0 + 8 * slot_cur, use_cur ^ 1, p.err, w_tempty, timed);
           __syncwarp();
           tc_fence_after();
-          const uint32_t phase = (row >> 7) & 7u;
           uint32_t hi[32], lo[32];
+          if (CIN8) {
+            // four taps x 8 channels -> the 32 columns of this K step; a pixel is 32 contiguous bytes
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 v = lds128(row + ((c ^ phase) << 4));
-            hi[4 * c + 0] = __float_as_uint(v.x); hi[4 * c + 1] = __float_as_uint(v.y);
-            hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
+            for (int j = 0; j < 4; ++j) {
+              const int rt = 4 * t + j;
+              const int pi = (rt < p.ntaps_real) ? p.g_plane[rt] : -1;
+              float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+              if (pi >= 0) {
+                const HaloPlane& pl = p.planes[pi];
+                const uint32_t px = abase + (uint32_t)(pl.smem_off + p.g_aoff[rt] + (g * pl.cols + r) * 32);
+                v0 = lds128(px); v1 = lds128(px + 16);
+              }
+              hi[8 * j + 0] = __float_as_uint(v0.x); hi[8 * j + 1] = __float_as_uint(v0.y);
+              hi[8 * j + 2] = __float_as_uint(v0.z); hi[8 * j + 3] = __float_as_uint(v0.w);
+              hi[8 * j + 4] = __float_as_uint(v1.x); hi[8 * j + 5] = __float_as_uint(v1.y);
+              hi[8 * j + 6] = __float_as_uint(v1.z); hi[8 * j + 7] = __float_as_uint(v1.w);
+            }
+          } else {
+            const uint32_t phase = (row >> 7) & 7u;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 v = lds128(row + ((c ^ phase) << 4));
+              hi[4 * c + 0] = __float_as_uint(v.x); hi[4 * c + 1] = __float_as_uint(v.y);
+              hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
+            }
           }
           const uint32_t taddr = t_ring + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot_cur * 64);
           tmem_st_x32(taddr, hi);
@@ -462,7 +488,10 @@ static bool halo_build(const ConvProblem* probs, int nclass, int n_tile_req, int
   memset(&prm, 0, sizeof(prm));
   prm.nclass = nclass;
   prm.nsplit = nsplit;
+  prm.cin8 = (p.Cin == 8) ? 1 : 0;
+  const int px_bytes = prm.cin8 ? 32 : 128;   // bytes of one pixel of a halo plane in shared memory
   prm.per_tap = ((p.Ho % kTileH) != 0 || (p.Wo % kTileW) != 0) ? 1 : 0;
+  if (prm.cin8 && (prm.per_tap || nclass != 1)) return false;
   int m_tiles = 0;
   if (prm.per_tap) {
     // one 128-pixel tile per (chunk, tap) step, tb images x th rows x tw columns (same tiling rule as conv_tc.cu)
@@ -523,7 +552,7 @@ static bool halo_build(const ConvProblem* probs, int nclass, int n_tile_req, int
     pl.cols = kTileW + pinfo[i].qx_max - pinfo[i].qx_min;
     pl.rows = kTileH + pinfo[i].qy_max - pinfo[i].qy_min;
     if (pl.cols > 256 || pl.rows > 256) return false;
-    pl.bytes = pl.rows * pl.cols * 128;
+    pl.bytes = pl.rows * pl.cols * px_bytes;
     pl.smem_off = off;
     off += (pl.bytes + 1023) / 1024 * 1024;
   }
@@ -533,10 +562,16 @@ static bool halo_build(const ConvProblem* probs, int nclass, int n_tile_req, int
     HaloTap& tp = prm.taps[t];
     const HaloPlane& pl = prm.planes[tinfo[t].plane];
     tp.plane = tinfo[t].plane;
-    tp.a_off = ((tinfo[t].qy - pl.qy_min) * pl.cols + (tinfo[t].qx - pl.qx_min)) * 128;
+    tp.a_off = ((tinfo[t].qy - pl.qy_min) * pl.cols + (tinfo[t].qx - pl.qx_min)) * px_bytes;
     tp.cls = tinfo[t].cls;
     tp.first = (tp.cls != last_cls) ? 1 : 0;
     last_cls = tp.cls;
+  }
+  if (prm.cin8) {   // regroup: one K step = four consecutive taps
+    prm.ntaps_real = prm.ntaps;
+    for (int t = 0; t < prm.ntaps_real; ++t) { prm.g_plane[t] = prm.taps[t].plane; prm.g_aoff[t] = prm.taps[t].a_off; }
+    prm.ntaps = (prm.ntaps_real + 3) / 4;
+    for (int t = 0; t < prm.ntaps; ++t) { prm.taps[t].plane = 0; prm.taps[t].a_off = 0; prm.taps[t].cls = 0; prm.taps[t].first = (t == 0) ? 1 : 0; }
   }
   prm.tiles_x = ceil_div(p.Wo, kTileW); prm.tiles_y = ceil_div(p.Ho, kTileH); prm.tiles_b = p.B;
   m_tiles = prm.tiles_x * prm.tiles_y * p.B;
@@ -567,7 +602,7 @@ static bool halo_build(const ConvProblem* probs, int nclass, int n_tile_req, int
   int cols = 32;
   while (cols < prm.nbuf * nclass * prm.acc_w + prm.st * 64) cols <<= 1;
   prm.tmem_cols = cols;
-  prm.k_chunks = p.Cin / 32;
+  prm.k_chunks = prm.cin8 ? 1 : p.Cin / 32;
   // weight ring slot = one (chunk, tap) block: [W_hi | W_lo] (3xTF32) or W_hi alone, 1024-byte aligned
   const int slot = (nsplit == 3) ? n_tile * 256 : (n_tile * 128 + 1023) / 1024 * 1024;
   prm.w_stage_bytes = slot;
@@ -601,10 +636,11 @@ static bool halo_build(const ConvProblem* probs, int nclass, int n_tile_req, int
                         (cuuint64_t)p.Hi * p.Wi * cp * 4};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   for (int i = 0; i < prm.nplanes; ++i) {
-    cuuint32_t box[5] = {32, (cuuint32_t)prm.planes[i].cols, 1, (cuuint32_t)prm.planes[i].rows, (cuuint32_t)(prm.per_tap ? prm.tb : 1)};
+    cuuint32_t box[5] = {(cuuint32_t)(prm.cin8 ? 8 : 32), (cuuint32_t)prm.planes[i].cols, 1, (cuuint32_t)prm.planes[i].rows,
+                         (cuuint32_t)(prm.per_tap ? prm.tb : 1)};
     CUresult r = enc(&plan.maps.m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(p.in), gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, prm.cin8 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return false;
   }
   for (int i = prm.nplanes; i < kMaxPlanes; ++i) plan.maps.m[i] = plan.maps.m[0];
@@ -613,8 +649,11 @@ static bool halo_build(const ConvProblem* probs, int nclass, int n_tile_req, int
 
 bool tc_halo_supported(const ConvProblem* probs, int nclass) {
   const ConvProblem& p = probs[0];
-  for (int c = 0; c < nclass; ++c)
-    if (!tc_layer_supported(probs[c])) return false;
+  for (int c = 0; c < nclass; ++c) {
+    ConvProblem q = probs[c];
+    if (q.Cin == 8 && q.in_pitch == 8) q.Cin = 32;   // 8-channel mode: everything but the channel rule must hold
+    if (!tc_layer_supported(q)) return false;
+  }
   // per-tap TS mode pays off for plain convolutions at low resolution; the 4-class transposed convolutions there are
   // TMEM-limited (single accumulator buffer, split N) and stay on the shared-memory-operand kernel (conv_tc.cu)
   if (((p.Ho % kTileH) != 0 || (p.Wo % kTileW) != 0) && nclass != 1) return false;
@@ -660,6 +699,10 @@ int tc_halo_prepare(TcLayer& t, const ConvProblem* probs, const float* const* w_
           const int co = nt * prm.n_tile + r;
           for (int k = 0; k < 32; ++k) {
             float w = 0.f;
+            if (prm.cin8) {   // K index = (tap within the group of four, channel)
+              const int rt = 4 * tt + k / 8;
+              if (co < p.Cout && rt < prm.ntaps_real) w = w_hosts[0][((size_t)rt * 8 + (k & 7)) * p.Cout_pad + co];
+            } else
             if (co < p.Cout) w = w_hosts[cls][((size_t)tap * p.Cin + kc * 32 + k) * p.Cout_pad + co];
             const float hi = (nsplit == 3) ? tf32_round_h(w) : w;
             const float lo = w - hi;
@@ -711,8 +754,9 @@ int conv_tc_halo_launch(const TcLayer& t, const ConvProblem* probs, cudaStream_t
   prm.timing = g_timing_dev;
   static bool attr_set = false;
   if (!attr_set) {
-    DEMON_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    DEMON_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    DEMON_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    DEMON_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    DEMON_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     attr_set = true;
   }
   int sms = 0, dev = 0;
@@ -720,8 +764,9 @@ int conv_tc_halo_launch(const TcLayer& t, const ConvProblem* probs, cudaStream_t
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (sms <= 0) sms = 148;
   const int grid = std::min(prm.total_tiles, sms);
-  if (prm.per_tap) conv_tc_halo_kernel<true><<<grid, kThreads, plan->smem_bytes, stream>>>(plan->maps, prm);
-  else conv_tc_halo_kernel<false><<<grid, kThreads, plan->smem_bytes, stream>>>(plan->maps, prm);
+  if (prm.per_tap) conv_tc_halo_kernel<true, false><<<grid, kThreads, plan->smem_bytes, stream>>>(plan->maps, prm);
+  else if (prm.cin8) conv_tc_halo_kernel<false, true><<<grid, kThreads, plan->smem_bytes, stream>>>(plan->maps, prm);
+  else conv_tc_halo_kernel<false, false><<<grid, kThreads, plan->smem_bytes, stream>>>(plan->maps, prm);
   DEMON_LAUNCH_CHECK();
   return DEMON_OK;
 }

@@ -85,6 +85,10 @@ struct demon_net {
   std::map<std::string, HostVar> host_vars;
   std::vector<void*> dev_allocs;
   int pipeline_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // CUDA graphs of demon_pipeline_forward, keyed by the pointer arguments (launch-bound at small batch: ~270 launches)
+  struct GraphEntry { std::vector<const void*> key; cudaGraphExec_t exec; int launches; };
+  std::vector<GraphEntry> graphs;
+  cudaStream_t cap_stream = nullptr;   // capture happens on this private stream (the caller's may be the legacy default stream)
   // optional per-layer timing with CUDA events on the launching stream (bench.py's roofline leg)
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;      // pairs (start, stop)
@@ -188,7 +192,8 @@ void build_dm_block(demon_net* n, const std::string& scope, bool iterative) {
 
 void build_refine_block(demon_net* n, const std::string& scope) {
   const std::string s = scope + "/";
-  n->add_layer(s + "conv0", L_CONV, n->rin, 0, 4, n->concat0, 32, 32, 3, 3, 1, 1, true);
+  Layer* c0 = n->add_layer(s + "conv0", L_CONV, n->rin, 0, 4, n->concat0, 32, 32, 3, 3, 1, 1, true);
+  c0->cin_buf = 8;
   n->add_layer(s + "conv1", L_CONV, n->concat0, 32, 32, n->rc1, 0, 64, 3, 3, 2, 2, true);
   n->add_layer(s + "conv1_1", L_CONV, n->rc1, 0, 64, n->concat1, 64, 64, 3, 3, 1, 1, true);
   n->add_layer(s + "conv2", L_CONV, n->concat1, 64, 64, n->rc2, 0, 128, 3, 3, 2, 2, true);
@@ -235,7 +240,7 @@ void build_plan(demon_net* n) {
   n->motion = n->add_buf(1, 1, 8);
   n->splitk = n->add_buf(1, 24, 1024);   // split-K partial sums [24][B][1024]
   const int RH = n->RH, RW = n->RW;
-  n->rin = n->add_buf(RH, RW, 4);
+  n->rin = n->add_buf(RH, RW, 8);   // [image1(3), depth upsampled(1), 0, 0, 0, 0]: 8 channels for the tensor-core 8-channel mode
   n->concat0 = n->add_buf(RH, RW, 64);
   n->rc1 = n->add_buf(RH / 2, RW / 2, 64);
   n->concat1 = n->add_buf(RH / 2, RW / 2, 128);
@@ -550,7 +555,8 @@ __global__ void __launch_bounds__(256) refine_input_kernel(const float* __restri
     // tf.image.resize_nearest_neighbor, align_corners=False: src = floor(dst * in / out)
     const int sy = (int)(((long)y * h) / H), sx = (int)(((long)x * w) / W);
     const float dv = __ldg(depth + n * d_sn + ((long)sy * w + sx) * d_sp);
-    reinterpret_cast<float4*>(rin)[i] = make_float4(__ldg(im), __ldg(im + img_sc), __ldg(im + 2 * img_sc), dv);
+    reinterpret_cast<float4*>(rin)[2 * i] = make_float4(__ldg(im), __ldg(im + img_sc), __ldg(im + 2 * img_sc), dv);
+    reinterpret_cast<float4*>(rin)[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -675,6 +681,8 @@ void demon_net_destroy(demon_net* n) {
   if (!n) return;
   for (void* p : n->dev_allocs) cudaFree(p);
   for (cudaEvent_t e : n->prof_events) cudaEventDestroy(e);
+  for (auto& g : n->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (n->cap_stream) cudaStreamDestroy(n->cap_stream);
   for (auto& l : n->layers) tc_layer_free(l->tc);
   cudaFree(n->ws);
   delete n;
@@ -747,14 +755,15 @@ int demon_net_finalize(demon_net* n) {
       const int nclass = build_problems(l, n->B, probs);
       bool all = true;
       for (int c = 0; c < nclass; ++c) all = all && tc_layer_supported(probs[c]);
-      if (all) {
+      const bool halo = use_halo_kernel() && tc_halo_supported(probs, nclass);   // also takes the 8-channel layers
+      if (all || halo) {
         std::vector<float> cls_w[4];
         const float* ptrs[4] = {nullptr, nullptr, nullptr, nullptr};
         for (int c = 0; c < nclass; ++c) {
           if (l.kind == L_CONV) pack_conv(l, k, cls_w[c]); else pack_deconv_class(l, k, c / 2, c % 2, cls_w[c]);
           ptrs[c] = cls_w[c].data();
         }
-        if (use_halo_kernel() && tc_halo_supported(probs, nclass)) rc = tc_halo_prepare(l.tc, probs, ptrs, nclass, n->precision);
+        if (halo) rc = tc_halo_prepare(l.tc, probs, ptrs, nclass, n->precision);
         else rc = tc_layer_prepare(l.tc, probs, ptrs, nclass, n->precision);
         if (rc) return rc;
         l.use_tc = true;
@@ -883,14 +892,8 @@ int demon_refine_forward(demon_net* n, const float* image1, const float* depth2,
   return run_refine_block(n, image1, 3 * P, 3, 1, depth2, (long)dh * dw, 1, dh, dw, depth0, (cudaStream_t)stream);
 }
 
-int demon_pipeline_forward(demon_net* n, const float* image_pair, const float* image2_2, int iterations, float* depth0, float* rotation,
-                           float* translation, float* flow2, float* depth2, float* normal2, void* stream) {
-  REQUIRE_READY(n);
-  DEMON_REQUIRE(image_pair, "pipeline: null image_pair");
-  DEMON_REQUIRE(iterations >= 0 && iterations <= 7, "pipeline: iterations %d", iterations);
-  DEMON_REQUIRE(n->RH == 192 && n->RW == 256, "pipeline: net was created with a %dx%d refinement block", n->RH, n->RW);
-  cudaStream_t s = (cudaStream_t)stream;
-  const int64_t launches0 = g_launch_count.load();
+static int pipeline_body(demon_net* n, const float* image_pair, const float* image2_2, int iterations, float* depth0, float* rotation,
+                         float* translation, float* flow2, float* depth2, float* normal2, cudaStream_t s) {
   int rc;
   if ((rc = import_image_pair(n, image_pair, 0, s))) return rc;
   if (image2_2) {
@@ -906,7 +909,56 @@ int demon_pipeline_forward(demon_net* n, const float* image_pair, const float* i
   }
   if ((rc = export_predictions(n, nullptr, flow2, depth2, normal2, rotation, translation, 0, s))) return rc;
   const long P = 192L * 256;
-  if ((rc = run_refine_block(n, image_pair, 6 * P, 1, P, n->dn2->p, 4L * 48 * 64, 4, 48, 64, depth0, s))) return rc;
+  return run_refine_block(n, image_pair, 6 * P, 1, P, n->dn2->p, 4L * 48 * 64, 4, 48, 64, depth0, s);
+}
+
+int demon_pipeline_forward(demon_net* n, const float* image_pair, const float* image2_2, int iterations, float* depth0, float* rotation,
+                           float* translation, float* flow2, float* depth2, float* normal2, void* stream) {
+  REQUIRE_READY(n);
+  DEMON_REQUIRE(image_pair, "pipeline: null image_pair");
+  DEMON_REQUIRE(iterations >= 0 && iterations <= 7, "pipeline: iterations %d", iterations);
+  DEMON_REQUIRE(n->RH == 192 && n->RW == 256, "pipeline: net was created with a %dx%d refinement block", n->RH, n->RW);
+  cudaStream_t s = (cudaStream_t)stream;
+  // The call is one CUDA graph per distinct set of pointer arguments (DEMON_GRAPH=0 disables): the first call with a new
+  // set runs eagerly, the second captures, later ones replay.  Not used while per-layer profiling is on or when the
+  // caller is itself capturing this stream.
+  static const bool graphs_on = []() { const char* e = getenv("DEMON_GRAPH"); return !(e && e[0] == '0'); }();
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s, &cap);
+  if (graphs_on && !n->profiling && cap == cudaStreamCaptureStatusNone) {
+    const std::vector<const void*> key = {image_pair, image2_2, depth0, rotation, translation, flow2, depth2, normal2,
+                                          reinterpret_cast<const void*>((intptr_t)iterations)};
+    for (auto& g : n->graphs)
+      if (g.key == key) {
+        if (g.exec == nullptr) {   // second call: capture
+          cudaGraph_t graph = nullptr;
+          const int64_t l0 = g_launch_count.load();
+          if (!n->cap_stream) DEMON_CHECK_CUDA(cudaStreamCreateWithFlags(&n->cap_stream, cudaStreamNonBlocking));
+          DEMON_CHECK_CUDA(cudaStreamBeginCapture(n->cap_stream, cudaStreamCaptureModeThreadLocal));
+          int rc = pipeline_body(n, image_pair, image2_2, iterations, depth0, rotation, translation, flow2, depth2, normal2, n->cap_stream);
+          cudaError_t e = cudaStreamEndCapture(n->cap_stream, &graph);
+          if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+          if (e != cudaSuccess) return fail(DEMON_E_CUDA, "pipeline: stream capture failed: %s", cudaGetErrorString(e));
+          g.launches = (int)(g_launch_count.load() - l0);
+          g_launch_count.fetch_sub(g.launches);   // counted again by the launch below
+          e = cudaGraphInstantiate(&g.exec, graph, 0);
+          cudaGraphDestroy(graph);
+          if (e != cudaSuccess) { g.exec = nullptr; return fail(DEMON_E_CUDA, "pipeline: graph instantiate failed: %s", cudaGetErrorString(e)); }
+        }
+        DEMON_CHECK_CUDA(cudaGraphLaunch(g.exec, s));
+        g_launch_count.fetch_add(g.launches);
+        n->pipeline_launches[iterations] = g.launches;
+        return DEMON_OK;
+      }
+    if (n->graphs.size() >= 32) {
+      for (auto& g : n->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+      n->graphs.clear();
+    }
+    n->graphs.push_back({key, nullptr, 0});
+  }
+  const int64_t launches0 = g_launch_count.load();
+  int rc = pipeline_body(n, image_pair, image2_2, iterations, depth0, rotation, translation, flow2, depth2, normal2, s);
+  if (rc) return rc;
   n->pipeline_launches[iterations] = (int)(g_launch_count.load() - launches0);
   return DEMON_OK;
 }
@@ -972,11 +1024,12 @@ static int standalone_conv(const float* in, float* out, int B, int H, int W, int
     build_problems(l, B, probs);
     bool all = true;
     for (int c = 0; c < nclass; ++c) all = all && tc_layer_supported(probs[c]);
-    if (!all) {
+    const bool halo = use_halo_kernel() && tc_halo_supported(probs, nclass);
+    if (!all && !halo) {
       for (void* q : tmp.dev_allocs) cudaFree(q);
       return fail(DEMON_E_INVALID, "conv test entry: shape not supported by the tcgen05 path");
     }
-    if (use_halo_kernel() && tc_halo_supported(probs, nclass)) rc = tc_halo_prepare(l.tc, probs, ptrs, nclass, precision);
+    if (halo) rc = tc_halo_prepare(l.tc, probs, ptrs, nclass, precision);
     else rc = tc_layer_prepare(l.tc, probs, ptrs, nclass, precision);
     if (rc) return rc;
     l.use_tc = true;

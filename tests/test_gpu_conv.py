@@ -112,6 +112,8 @@ def test_simt_deconv_matches_float64(case):
 
 # shapes the tcgen05 path takes (Cin % 32 == 0, Cout >= 16)
 TC_CASES = [
+    (2, 32, 16, 8, 32, 9, 1, 2, 1),      # conv1y: 8-channel mode (4 taps per K step)
+    (1, 32, 24, 8, 32, 3, 3, 1, 1),      # netRefine/conv0 (4 -> 8 padded channels)
     (2, 12, 40, 32, 32, 1, 9, 1, 2),     # conv1x
     (2, 24, 16, 32, 32, 7, 1, 2, 1),     # conv2y
     (2, 8, 16, 64, 64, 3, 1, 1, 1),      # conv2_1y

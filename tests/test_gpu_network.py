@@ -90,9 +90,10 @@ def test_variable_table_agrees_with_python_table(sessions):
 
 def test_tensor_core_path_is_selected_for_the_big_layers(sessions):
     net = sessions["3xtf32"].net(1)
-    for layer in ("netRefine/conv1_1", "netFlow1/conv3x", "netDM2/refine3/upconv", "netRefine/refine0/upconv"):
+    for layer in ("netRefine/conv1_1", "netFlow1/conv3x", "netDM2/refine3/upconv", "netRefine/refine0/upconv", "netFlow1/conv1y",
+                  "netRefine/conv0"):
         assert net.uses_tensor_cores(layer), layer
-    for layer in ("netFlow1/conv1y", "netDM1/motion_fc1", "netRefine/predict_depth0/conv2"):
+    for layer in ("netDM1/conv2_extra_inputsy", "netDM1/motion_fc1", "netRefine/predict_depth0/conv2"):
         assert not net.uses_tensor_cores(layer), layer
     assert not sessions["fp32"].net(1).uses_tensor_cores("netRefine/conv1_1")
 
@@ -198,10 +199,36 @@ def test_pipeline_matches_stagewise_api_and_median_image2_2(sessions, random_pai
     assert np.array_equal(d0h.numpy(), d0) and np.array_equal(rot.numpy(), r["predict_rotation"])
 
 
+def test_cuda_graph_replay_equals_eager(sessions, random_pairs):
+    """demon_pipeline_forward replays a CUDA graph from the third call with the same pointer arguments on; the result
+    must equal the eager first call bit for bit, also after the input buffer's CONTENT changes."""
+    from demon_b200.networks_original import DemonPipeline
+    ip, i22 = random_pairs
+    pipe = DemonPipeline(sessions["3xtf32"], batch_size=2, iterations=3)
+    x = torch.from_numpy(ip).cuda()
+    x2 = torch.from_numpy(i22).cuda()
+    eager = {k: v.clone() for k, v in pipe.forward(x, x2).items()}          # fresh outputs -> eager
+    outs = {k: torch.empty_like(v) for k, v in eager.items()}
+    for _ in range(4):                                                       # eager, capture, replay, replay
+        pipe.forward(x, x2, outs)
+    torch.cuda.synchronize()
+    for k in eager:
+        assert torch.equal(eager[k], outs[k]), k
+    flipped = torch.flip(x, dims=[0]).contiguous()
+    ref = {k: v.clone() for k, v in pipe.forward(flipped, torch.flip(x2, dims=[0]).contiguous()).items()}
+    x.copy_(flipped); x2.copy_(torch.flip(x2, dims=[0]))
+    pipe.forward(x, x2, outs)                                                # replay on new content
+    torch.cuda.synchronize()
+    for k in ref:
+        assert torch.equal(ref[k], outs[k]), k
+
+
 def test_batch_consistency_and_determinism_at_benchmark_batch(sessions, synthetic_weights):
-    """BASELINE.json configs[2] size (batch 64): every sample equals the batch-1 result of the same pair
-    (pairs are independent, blocks_original.py has no cross-sample op), two runs are bit identical, and a
-    sample checked against the CPU oracle is inside the tolerance."""
+    """BASELINE.json configs[2] size (batch 64): two runs are bit identical; every sample equals the batch-1
+    result of the same pair (pairs are independent, blocks_original.py has no cross-sample op) up to fp32
+    rounding -- the tensor-core path picks its N tile, and with it how the 3xTF32 terms are summed, from the
+    number of tiles a layer has, so different batch sizes are not bit identical; and a sample checked against the
+    CPU oracle is inside the tolerance."""
     from demon_b200.networks_original import DemonPipeline
     g = torch.Generator().manual_seed(1234)
     ip = (torch.rand(64, 6, 192, 256, generator=g) - 0.5)
@@ -218,8 +245,8 @@ def test_batch_consistency_and_determinism_at_benchmark_batch(sessions, syntheti
     for i in (0, 37, 63):
         o = one.forward(x[i:i + 1], None)
         torch.cuda.synchronize()
-        assert torch.equal(o["predict_depth0"][0], a["predict_depth0"][i]), i
-        assert torch.equal(o["predict_translation"][0], a["predict_translation"][i]), i
+        assert l1_rel(o["predict_depth0"][0].cpu().numpy(), a["predict_depth0"][i].cpu().numpy()) < 2e-6, i
+        np.testing.assert_allclose(o["predict_translation"][0].cpu().numpy(), a["predict_translation"][i].cpu().numpy(), atol=2e-6)
     i = 37
     ipn = ip[i:i + 1].numpy()
     i22 = oops.median3x3_downsample(oops.median3x3_downsample(np.ascontiguousarray(ipn[:, 3:6])))

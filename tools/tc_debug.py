@@ -84,6 +84,9 @@ def report(name, got, want):
 def main():
     rng = np.random.RandomState(0)
     halo_cases = [
+        ("CIN8 9x1 s2 32x16->16x16 Cout32", 2, 32, 16, 8, 32, 9, 1, 2, 1),
+        ("CIN8 3x3 16x16 Cout32", 1, 16, 16, 8, 32, 3, 3, 1, 1),
+        ("CIN8 9x1 s2 192x256 Cout32 B2", 2, 192, 256, 8, 32, 9, 1, 2, 1),
         ("HALO 1x1 16x8 Cin32 Cout32", 1, 16, 8, 32, 32, 1, 1, 1, 1),
         ("HALO 3x1 16x8 Cin32 Cout32", 1, 16, 8, 32, 32, 3, 1, 1, 1),
         ("HALO 1x3 16x8 Cin32 Cout32", 1, 16, 8, 32, 32, 1, 3, 1, 1),
