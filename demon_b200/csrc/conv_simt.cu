@@ -165,6 +165,50 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvProblem p) {
   }
 }
 
+// Direct convolution for the prediction heads' last layers (Cout <= 4, Cin <= 32, e.g. 24 -> 4 and 16 -> 1, 3x3): one thread
+// per output pixel, weights in shared memory, the taps' pixels come through L1 (every input pixel is read by up to 9
+// neighbouring threads of the same CTA row).  These layers have ~150 MACs per pixel: the implicit-GEMM tile machinery
+// above costs more than the arithmetic.  grid (ceil(Wo/128), Ho, B).
+template <int COUT>
+__global__ void __launch_bounds__(128) conv_small_cout_kernel(const ConvProblem p) {
+  __shared__ float ws[kMaxTaps * 32 * COUT];
+  const int nw = p.ntaps * p.Cin;
+  for (int i = threadIdx.x; i < nw * COUT; i += 128) {
+    const int k = i / COUT, co = i - k * COUT;
+    ws[i] = (co < p.Cout) ? __ldg(p.w + (size_t)k * p.Cout_pad + co) : 0.f;
+  }
+  __syncthreads();
+  const int ox = blockIdx.x * 128 + threadIdx.x, oy = blockIdx.y, n = blockIdx.z;
+  if (ox >= p.Wo) return;
+  float acc[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+  for (int t = 0; t < p.ntaps; ++t) {
+    const int iy = oy * p.sy + p.dy[t], ix = ox * p.sx + p.dx[t];
+    if (iy < 0 || iy >= p.Hi || ix < 0 || ix >= p.Wi) continue;
+    const float4* src = reinterpret_cast<const float4*>(p.in + ((size_t)(n * p.Hi + iy) * p.Wi + ix) * p.in_pitch);
+    const float* wt = ws + (size_t)t * p.Cin * COUT;
+    for (int c4 = 0; c4 < p.Cin / 4; ++c4) {
+      const float4 v = __ldg(src + c4);
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) acc[c] = fmaf(vv[j], wt[(c4 * 4 + j) * COUT + c], acc[c]);
+    }
+  }
+  float* o = p.out + ((size_t)(n * p.Hfull + oy * p.osy + p.ooy) * p.Wfull + ox * p.osx + p.oox) * p.out_pitch;
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) {
+    if (c < p.Cout) {
+      float x = acc[c] + __ldg(p.bias + c);
+      if (p.leaky) x = fmaxf(0.1f * x, x);
+      if (c == 0 && p.scale != nullptr) x *= __ldg(p.scale + (size_t)n * p.scale_stride);
+      o[c] = x;
+    }
+  }
+}
+
 // out[m][c] = act(bias[c] + sum_z partial[z][m][c]); only used for 1x1 problems on 1x1 images (dense layers)
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const ConvProblem p, int ksplit, int M) {
   const int i = blockIdx.x * 256 + threadIdx.x;
@@ -188,6 +232,13 @@ int conv_simt_launch(const ConvProblem& p, cudaStream_t stream) {
   const int64_t M = (int64_t)p.B * p.Ho * p.Wo;
   DEMON_REQUIRE(M < (1ll << 31), "conv: too many output pixels");
   if (M == 0 || p.Cout == 0) return DEMON_OK;
+  if (p.Cout <= 4 && p.Cin <= 32 && p.ntaps > 1 && p.partial == nullptr && p.Ho <= 65535 && p.B <= 65535) {
+    dim3 grid(ceil_div(p.Wo, 128), p.Ho, p.B);
+    if (p.Cout == 1) conv_small_cout_kernel<1><<<grid, 128, 0, stream>>>(p);
+    else conv_small_cout_kernel<4><<<grid, 128, 0, stream>>>(p);
+    DEMON_LAUNCH_CHECK();
+    return DEMON_OK;
+  }
   const int ks = (p.partial != nullptr && p.ksplit > 1) ? p.ksplit : 1;
   if (ks > 1) DEMON_REQUIRE(p.Hi == 1 && p.Wi == 1 && p.Ho == 1 && p.Wo == 1, "conv: split-K is for dense layers only");
   ConvProblem q = p;

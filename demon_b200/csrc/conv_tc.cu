@@ -84,7 +84,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int S = p.stages;
   const uint32_t full0 = smem_u32(&bars[0]), split0 = smem_u32(&bars[8]), empty0 = smem_u32(&bars[16]);
   const uint32_t afull0 = smem_u32(&bars[24]), aempty0 = smem_u32(&bars[26]);
-  const uint32_t tmem_cols = p.n_tile <= 16 ? 32 : (p.n_tile <= 32 ? 64 : (p.n_tile <= 64 ? 128 : (p.n_tile <= 128 ? 256 : 512)));
+  // stacked 3xTF32 (N <= 128): D[:, 0:2N] (+)= A_hi * [W_hi ; W_lo] as ONE UMMA of N' = 2N, D[:, N:2N] += A_lo * W_hi, the
+  // epilogue adds the halves -- two instructions per K8 step instead of three (conv_tc_halo.cu has the measurements)
+  const bool stacked = (p.nsplit == 3) && (p.n_tile <= 128);
+  const int acc_w = stacked ? 2 * p.n_tile : p.n_tile;
+  const uint32_t tmem_cols = 2 * acc_w <= 32 ? 32 : (2 * acc_w <= 64 ? 64 : (2 * acc_w <= 128 ? 128 : (2 * acc_w <= 256 ? 256 : 512)));
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
@@ -133,13 +137,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t idesc = umma_idesc_tf32(p.n_tile);
+      const uint32_t idesc = umma_idesc_tf32(p.n_tile), idesc2 = umma_idesc_tf32(2 * p.n_tile);
       int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int a = it & 1;
         mbar_wait(aempty0 + 8 * a, ((it >> 1) & 1) ^ 1, p.err);   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.n_tile);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * acc_w);
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(full0 + 8 * stage, phase, p.err);
           tc_fence_after();
@@ -150,14 +154,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
           for (int j = 0; j < 4; ++j) {   // 4 x K8 = 32 channels; +32 bytes per K8 step inside the swizzled row
             const uint64_t adv = (uint64_t)(2 * j);
-            if (p.nsplit == 3) umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, (ks | j) != 0);
-            umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, (p.nsplit == 3) ? 1u : (uint32_t)((ks | j) != 0));
+            if (stacked) {
+              umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc2, (ks | j) != 0);
+            } else {
+              if (p.nsplit == 3) umma_tf32(d_tmem, a_hi + adv, w_lo + adv, idesc, (ks | j) != 0);
+              umma_tf32(d_tmem, a_hi + adv, w_hi + adv, idesc, (p.nsplit == 3) ? 1u : (uint32_t)((ks | j) != 0));
+            }
           }
           if (p.nsplit == 3) {
             mbar_wait(split0 + 8 * stage, phase, p.err);
             tc_fence_after();
+            const uint32_t d_lo = stacked ? d_tmem + (uint32_t)p.n_tile : d_tmem;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) umma_tf32(d_tmem, a_lo + (uint64_t)(2 * j), w_hi + (uint64_t)(2 * j), idesc, 1);
+            for (int j = 0; j < 4; ++j) umma_tf32(d_lo, a_lo + (uint64_t)(2 * j), w_hi + (uint64_t)(2 * j), idesc, 1);
           }
           umma_commit(empty0 + 8 * stage);                 // frees the smem stage when these MMAs are done
           if (ks == ksteps - 1) umma_commit(afull0 + 8 * a);   // accumulator complete
@@ -200,12 +209,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int n = n0 + nl, oy = y0 + yl, ox = x0 + xl;
       const bool valid = n < p.B && oy < p.Ho && ox < p.Wo;
       float* orow = p.out + ((size_t)(n * p.Hfull + oy * p.osy + p.cls_ooy[cls]) * p.Wfull + ox * p.osx + p.cls_oox[cls]) * p.out_pitch;
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.n_tile);
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * acc_w);
       const int cbase = nt * p.n_tile;
       for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
         uint32_t v[32];
         const int ncol = (p.n_tile - c0) >= 32 ? 32 : 16;
         if (ncol == 32) tmem_ld_x32(t_row + c0, v); else tmem_ld_x16(t_row + c0, v);
+        if (stacked) {   // big term + small terms
+          uint32_t u[32];
+          if (ncol == 32) tmem_ld_x32(t_row + p.n_tile + c0, u); else tmem_ld_x16(t_row + p.n_tile + c0, u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
+        }
         tmem_ld_wait();
         if (valid) {
 #pragma unroll
