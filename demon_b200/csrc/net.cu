@@ -390,6 +390,13 @@ int run_layer(const Layer& l, int B, cudaStream_t stream, float* splitk_ws = nul
 
 int run_layer_profiled(demon_net* n, int idx, cudaStream_t stream) {
   const Layer& l = *n->layers[idx];
+  static const bool sync_layers = getenv("DEMON_SYNC_LAYERS") && atoi(getenv("DEMON_SYNC_LAYERS")) != 0;   // debugging aid
+  if (sync_layers) {
+    int rc = run_layer(l, n->B, stream, n->splitk->p);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (rc == DEMON_OK && e != cudaSuccess) return fail(DEMON_E_CUDA, "layer %s: %s", l.name.c_str(), cudaGetErrorString(e));
+    return rc;
+  }
   if (!n->profiling) return run_layer(l, n->B, stream, n->splitk->p);
   if (n->prof_used + 2 > n->prof_events.size()) {
     const size_t old = n->prof_events.size();
@@ -963,8 +970,21 @@ int demon_pipeline_forward(demon_net* n, const float* image_pair, const float* i
   return DEMON_OK;
 }
 
+static int pipeline_host(demon_net* n, const float* image_pair_host, const float* image2_2_host, int iterations, float* depth0_host,
+                         float* rotation_host, float* translation_host, void* stream, bool sync);
+
 int demon_pipeline_forward_host(demon_net* n, const float* image_pair_host, const float* image2_2_host, int iterations, float* depth0_host,
                                 float* rotation_host, float* translation_host, void* stream) {
+  return pipeline_host(n, image_pair_host, image2_2_host, iterations, depth0_host, rotation_host, translation_host, stream, true);
+}
+
+int demon_pipeline_forward_host_async(demon_net* n, const float* image_pair_host, const float* image2_2_host, int iterations,
+                                      float* depth0_host, float* rotation_host, float* translation_host, void* stream) {
+  return pipeline_host(n, image_pair_host, image2_2_host, iterations, depth0_host, rotation_host, translation_host, stream, false);
+}
+
+static int pipeline_host(demon_net* n, const float* image_pair_host, const float* image2_2_host, int iterations, float* depth0_host,
+                         float* rotation_host, float* translation_host, void* stream, bool sync) {
   REQUIRE_READY(n);
   DEMON_REQUIRE(image_pair_host && depth0_host, "pipeline_host: null pointer");
   cudaStream_t s = (cudaStream_t)stream;
@@ -987,7 +1007,7 @@ int demon_pipeline_forward_host(demon_net* n, const float* image_pair_host, cons
   if (rotation_host) DEMON_CHECK_CUDA(cudaMemcpyAsync(rotation_host, rt_dev, (size_t)n->B * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (translation_host)
     DEMON_CHECK_CUDA(cudaMemcpyAsync(translation_host, rt_dev + 3 * n->B, (size_t)n->B * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
-  DEMON_CHECK_CUDA(cudaStreamSynchronize(s));
+  if (sync) DEMON_CHECK_CUDA(cudaStreamSynchronize(s));
   return DEMON_OK;
 }
 

@@ -219,11 +219,13 @@ class RefinementNet(_NetBase):
 class DemonPipeline:
     """examples/example.py:87-99 as one device-resident call (channels_first only)."""
 
-    def __init__(self, session=None, batch_size=1, iterations=3):
+    def __init__(self, session=None, batch_size=1, iterations=3, private_net=False):
         self.session = session if session is not None else default_session()
         self.batch_size = int(batch_size)
         self.iterations = int(iterations)
-        self.net = self.session.net(self.batch_size)
+        # private_net: an own network handle (own workspace), so that two pipelines can be in flight on two streams
+        self.net = (_NetHandle(self.session.weights, self.batch_size, (192, 256), self.session.precision) if private_net
+                    else self.session.net(self.batch_size))
 
     def forward(self, image_pair, image2_2=None, outputs=None):
         """image_pair: torch CUDA [B,6,192,256]; image2_2: torch CUDA [B,3,48,64] or None (then it is
@@ -254,6 +256,18 @@ class DemonPipeline:
             return x.data_ptr() if isinstance(x, torch.Tensor) else x.ctypes.data
         _lib.check(_lib.load().demon_pipeline_forward_host(
             self.net.ptr, hp(image_pair), hp(image2_2), self.iterations, hp(depth0), hp(rotation), hp(translation), _stream()))
+
+    def forward_host_async(self, image_pair, image2_2, depth0, rotation, translation, stream=None):
+        """forward_host without the final synchronisation, on `stream` (a torch.cuda.Stream; default: current).  The host
+        buffers must be pinned and are valid after `stream.synchronize()`.  Two DemonPipeline objects on two Sessions'
+        nets and two streams overlap one batch's copies with the other's compute."""
+        def hp(x):
+            if x is None:
+                return None
+            return x.data_ptr() if isinstance(x, torch.Tensor) else x.ctypes.data
+        s = ctypes.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)
+        _lib.check(_lib.load().demon_pipeline_forward_host_async(
+            self.net.ptr, hp(image_pair), hp(image2_2), self.iterations, hp(depth0), hp(rotation), hp(translation), s))
 
     def launches(self):
         return _lib.load().demon_net_pipeline_launches(self.net.ptr, self.iterations)

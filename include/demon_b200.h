@@ -159,6 +159,11 @@ int demon_pipeline_forward(demon_net* net, const float* image_pair, const float*
 int demon_pipeline_forward_host(demon_net* net, const float* image_pair_host, const float* image2_2_host,
                                 int iterations, float* depth0_host, float* rotation_host,
                                 float* translation_host, void* stream);
+/* Same without the final synchronisation: the host outputs are valid once `stream` has been synchronised.  With PINNED
+ * host buffers and two nets on two streams a caller overlaps the copies of one batch with the compute of the other. */
+int demon_pipeline_forward_host_async(demon_net* net, const float* image_pair_host, const float* image2_2_host,
+                                      int iterations, float* depth0_host, float* rotation_host,
+                                      float* translation_host, void* stream);
 
 /* introspection for tests and bench */
 int demon_net_batch(const demon_net* net);

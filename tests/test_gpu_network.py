@@ -197,6 +197,18 @@ def test_pipeline_matches_stagewise_api_and_median_image2_2(sessions, random_pai
     rot, tr = torch.empty(2, 3).pin_memory(), torch.empty(2, 3).pin_memory()
     pipe.forward_host(hp, None, d0h, rot, tr)
     assert np.array_equal(d0h.numpy(), d0) and np.array_equal(rot.numpy(), r["predict_rotation"])
+    # async entry, two pipelines (own workspaces) in flight on two streams: same bits
+    pipes = [pipe, DemonPipeline(s, batch_size=2, iterations=3, private_net=True)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [(torch.zeros(2, 1, 192, 256).pin_memory(), torch.zeros(2, 3).pin_memory(), torch.zeros(2, 3).pin_memory())
+            for _ in range(2)]
+    for i in range(6):
+        k = i % 2
+        streams[k].synchronize()
+        pipes[k].forward_host_async(hp, None, *outs[k], stream=streams[k])
+    torch.cuda.synchronize()
+    for k in range(2):
+        assert np.array_equal(outs[k][0].numpy(), d0) and np.array_equal(outs[k][2].numpy(), r["predict_translation"])
 
 
 def test_cuda_graph_replay_equals_eager(sessions, random_pairs):
