@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
       mbar_init(aempty0 + 8 * s, (uint32_t)p.aempty_count);
     }
     for (int s = 0; s < kMaxTStages; ++s) {
-      mbar_init(tfull0 + 8 * s, 4);
+      mbar_init(tfull0 + 8 * s, 4 + 1);   // the four warps of the owning stager group + the W producer's expect_tx
       mbar_init(tempty0 + 8 * s, 1);
     }
     for (int s = 0; s < kMaxWStages; ++s) {
@@ -206,8 +206,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
     }
   } else if (warp == kWProducerWarp) {
     // ===== W producer: one weight block per (chunk, tap), its own ring ====================================================
+    // The copy's bytes complete on the STEP's barrier (the one the stager group arrives on), so the MMA thread polls one
+    // barrier per step instead of two (a completed poll costs it ~150 cycles, tools/umma_contention_probe.cu).  The weight
+    // ring is at most as deep as the A-operand ring (sw <= st): once W_empty of step s - sw has been committed, step
+    // s - st has long been consumed, i.e. the step barrier is in the phase this expect_tx belongs to.
     if (elect_one_sync()) {
-      int sw = 0;
+      int sw = 0, ts = 0;
       uint32_t pw = 0;
       long long w_wempty = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -215,10 +219,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
         const unsigned char* wsrc = p.w + (size_t)nt * steps_per_tile * p.w_stage_bytes;
         for (int kt = 0; kt < steps_per_tile; ++kt) {
           wait_t(wempty0 + 8 * sw, pw ^ 1, p.err, w_wempty, timed);
-          mbar_expect_tx(wfull0 + 8 * sw, (uint32_t)p.w_stage_bytes);
+          mbar_expect_tx(tfull0 + 8 * ts, (uint32_t)p.w_stage_bytes);
           bulk_load(smem_u32(w_ring + (size_t)sw * p.w_stage_bytes), wsrc + (size_t)kt * p.w_stage_bytes, (uint32_t)p.w_stage_bytes,
-                    wfull0 + 8 * sw);
+                    tfull0 + 8 * ts);
           if (++sw == p.sw) { sw = 0; pw ^= 1; }
+          if (++ts == p.st) ts = 0;
         }
       }
       if (timed) p.timing[blockIdx.x * 16 + 1] = w_wempty;
@@ -230,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
     // when the phase is already complete), and the per-tap class / first-of-class flags live in two register bitmasks.
     if (elect_one_sync()) {
       int st = 0, sw = 0;
-      uint32_t pt = 0, pw = 0;
+      uint32_t pt = 0;
       // 3xTF32 as TWO instructions per K8 step when N <= 64 ("stacked"): the weight block holds [W_hi ; W_lo] as 2N
       // consecutive rows, so
       //   D[:, 0:2N]  (+)= A_hi * [W_hi ; W_lo]      (one UMMA of N' = 2N: big term | first small term)
@@ -242,10 +247,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
       for (int t = 0; t < p.ntaps; ++t) { cls_bits |= (uint32_t)p.taps[t].cls << (2 * t); first_bits |= (uint32_t)p.taps[t].first << t; }
       const uint32_t w_lo_off = (uint32_t)p.n_tile * 128u;
       const uint32_t w_ring_addr = smem_u32(w_ring);
-      long long w_cempty = 0, w_tfull = 0, w_wfull = 0;
+      long long w_cempty = 0, w_tfull = 0;
       const long long t_begin = clock64();
       int it = 0;
-      bool rdy_t = mbar_try(tfull0, 0), rdy_w = mbar_try(wfull0, 0);
+      bool rdy_t = mbar_try(tfull0, 0);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int a = (p.nbuf == 2) ? (it & 1) : 0;
         const uint32_t cphase = (p.nbuf == 2) ? ((it >> 1) & 1) : (it & 1);
@@ -254,16 +259,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           for (int t = 0; t < p.ntaps; ++t) {
             if (!rdy_t) wait_t(tfull0 + 8 * st, pt, p.err, w_tfull, timed);
-            if (!rdy_w) wait_t(wfull0 + 8 * sw, pw, p.err, w_wfull, timed);
             tc_fence_after();
             const uint32_t a_hi = t_ring + (uint32_t)(st * 64), a_lo = a_hi + 32;
             const uint32_t wbase = w_ring_addr + (uint32_t)(sw * p.w_stage_bytes);
             const int st_cur = st, sw_cur = sw;
             if (++st == p.st) { st = 0; pt ^= 1; }
-            if (++sw == p.sw) { sw = 0; pw ^= 1; }
-            // poll the NEXT step's barriers now; the answers are consumed after this step's MMAs have been issued
-            rdy_t = mbar_try(tfull0 + 8 * st, pt);
-            rdy_w = mbar_try(wfull0 + 8 * sw, pw);
+            if (++sw == p.sw) sw = 0;
+            rdy_t = mbar_try(tfull0 + 8 * st, pt);   // poll the NEXT step's barrier
             const uint64_t w_hi = umma_desc_sw128_sbo(wbase, 1024);
             const uint32_t d_tmem = d_base + ((cls_bits >> (2 * t)) & 3u) * (uint32_t)p.acc_w;
             const bool fresh = (kc == 0) && ((first_bits >> t) & 1u);
@@ -293,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
       }
       if (timed) {
         long long* tm = p.timing + blockIdx.x * 16;
-        tm[2] = w_cempty; tm[3] = w_tfull; tm[5] = w_wfull; tm[9] = clock64() - t_begin;
+        tm[2] = w_cempty; tm[3] = w_tfull; tm[5] = 0; tm[9] = clock64() - t_begin;
       }
     }
   } else if (warp < 2 + kStagerWarps) {
@@ -341,10 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
           } else {
             row = 0;
           }
-          wait_t(tempty0 + 8 * slot_cur, use_cur ^ 1, p.err, w_tempty, timed);
-          __syncwarp();
-          tc_fence_after();
-          uint32_t hi[32], lo[32];
+          uint32_t hi[32], lo[32];   // the shared-memory loads are in flight while the slot's barrier is polled
           if (CIN8) {
             // four taps x 8 channels -> the 32 columns of this K step; a pixel is 32 contiguous bytes
 #pragma unroll
@@ -371,6 +370,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
               hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
             }
           }
+          wait_t(tempty0 + 8 * slot_cur, use_cur ^ 1, p.err, w_tempty, timed);
+          __syncwarp();
+          tc_fence_after();
           const uint32_t taddr = t_ring + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot_cur * 64);
           tmem_st_x32(taddr, hi);
           if (p.nsplit == 3) {
@@ -612,7 +614,7 @@ static bool halo_build(const ConvProblem* probs, int nclass, int n_tile_req, int
   while (prm.sa > 2 && budget - prm.sa * prm.a_region_bytes < 4 * slot) --prm.sa;
   const int rest = budget - prm.sa * prm.a_region_bytes;
   if (rest < 2 * slot) return false;
-  prm.sw = std::min(kMaxWStages, rest / slot);
+  prm.sw = std::min(std::min(kMaxWStages, prm.st), rest / slot);   // sw <= st, see the W producer
   plan.smem_bytes = prm.sa * prm.a_region_bytes + prm.sw * slot + 1024;
   prm.B = p.B;
   prm.total_tiles = m_tiles * prm.n_tiles;
