@@ -43,24 +43,42 @@ __global__ void __launch_bounds__(128) warp2d_kernel(const T* __restrict__ in, c
   WarpTap<T> t = warp2d_tap<T>(x, y, __ldg(d), __ldg(d + hw), W, H, normalized);
   const T* src = in + (size_t)n * C * hw;
   T* dst = out + (size_t)n * C * hw + (size_t)y * W + x;
+  // channels in chunks of four: the sixteen gathers of a chunk are in flight before the first blend
+  constexpr int CH = 4;
   if (CLAMP) {
     const int x1i = (int)((unsigned)t.x0 + 1u), y1i = (int)((unsigned)t.y0 + 1u);
     const int x0 = clampi(t.x0, W), x1 = clampi(x1i, W), y0 = clampi(t.y0, H), y1 = clampi(y1i, H);
-    for (int c = 0; c < C; ++c) {
-      const T* p = src + (size_t)c * hw;
-      T v0 = __ldg(p + (size_t)y0 * W + x0), v1 = __ldg(p + (size_t)y0 * W + x1);
-      T v2 = __ldg(p + (size_t)y1 * W + x0), v3 = __ldg(p + (size_t)y1 * W + x1);
-      dst[(size_t)c * hw] = warp2d_blend(v0, v1, v2, v3, t);
+    const size_t o00 = (size_t)y0 * W + x0, o01 = (size_t)y0 * W + x1, o10 = (size_t)y1 * W + x0, o11 = (size_t)y1 * W + x1;
+    for (int c0 = 0; c0 < C; c0 += CH) {
+      T v[CH][4];
+#pragma unroll
+      for (int k = 0; k < CH; ++k)
+        if (c0 + k < C) {
+          const T* p = src + (size_t)(c0 + k) * hw;
+          v[k][0] = __ldg(p + o00); v[k][1] = __ldg(p + o01); v[k][2] = __ldg(p + o10); v[k][3] = __ldg(p + o11);
+        }
+#pragma unroll
+      for (int k = 0; k < CH; ++k)
+        if (c0 + k < C) dst[(size_t)(c0 + k) * hw] = warp2d_blend(v[k][0], v[k][1], v[k][2], v[k][3], t);
     }
   } else {
     const bool valid = warp2d_valid(t.x0, t.y0, W, H);
-    for (int c = 0; c < C; ++c) {
-      T r = border_value;
-      if (valid) {
-        const T* p = src + (size_t)c * hw + (size_t)t.y0 * W + t.x0;
-        r = warp2d_blend(__ldg(p), __ldg(p + 1), __ldg(p + W), __ldg(p + W + 1), t);
-      }
-      dst[(size_t)c * hw] = r;
+    if (!valid) {
+      for (int c = 0; c < C; ++c) dst[(size_t)c * hw] = border_value;
+      return;
+    }
+    const T* p0 = src + (size_t)t.y0 * W + t.x0;
+    for (int c0 = 0; c0 < C; c0 += CH) {
+      T v[CH][4];
+#pragma unroll
+      for (int k = 0; k < CH; ++k)
+        if (c0 + k < C) {
+          const T* p = p0 + (size_t)(c0 + k) * hw;
+          v[k][0] = __ldg(p); v[k][1] = __ldg(p + 1); v[k][2] = __ldg(p + W); v[k][3] = __ldg(p + W + 1);
+        }
+#pragma unroll
+      for (int k = 0; k < CH; ++k)
+        if (c0 + k < C) dst[(size_t)(c0 + k) * hw] = warp2d_blend(v[k][0], v[k][1], v[k][2], v[k][3], t);
     }
   }
 }
@@ -85,8 +103,10 @@ static int warp2d_launch(const T* in, const T* disp, T* out, int n, int c, int h
 
 // ---------------------------------------------------------------------------------------------
 // depth_to_flow (replaces depthtoflow.cc:250-313 / depthtoflow_cuda.cu:62-126 + rotation_format.cu)
-// grid (ceil(HW/256), N): the per-sample camera (Rodrigues etc.) is computed once per CTA by thread 0.
+// grid (ceil(HW/(256*8)), N): the per-sample camera (Rodrigues etc.) is computed once per CTA by thread 0 and used for
+// eight pixels per thread (a CTA per 256 pixels spent most of its time in that set-up).
 // ---------------------------------------------------------------------------------------------
+constexpr int kPixPerThread = 8;
 template <class T>
 __global__ void __launch_bounds__(256) depth_to_flow_kernel(const T* __restrict__ depth, const T* __restrict__ intrinsics,
                                                            const T* __restrict__ rotation, const T* __restrict__ translation,
@@ -99,13 +119,25 @@ __global__ void __launch_bounds__(256) depth_to_flow_kernel(const T* __restrict_
                rotation_format, W, H);
   __syncthreads();
   const int hw = H * W;
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= hw) return;
-  const int y = i / W, x = i - y * W;
-  T fx, fy;
-  d2f_pixel(fx, fy, __ldg(depth + (size_t)n * hw + i), x, y, cam, inverse_depth, normalize_flow);
-  flow[(size_t)n * 2 * hw + i] = fx;
-  flow[(size_t)n * 2 * hw + hw + i] = fy;
+  const T* dn = depth + (size_t)n * hw;
+  T* fn = flow + (size_t)n * 2 * hw;
+  T dv[kPixPerThread];
+#pragma unroll
+  for (int k = 0; k < kPixPerThread; ++k) {   // all loads first
+    const int i = (blockIdx.x * kPixPerThread + k) * 256 + threadIdx.x;
+    dv[k] = (i < hw) ? __ldg(dn + i) : (T)1;
+  }
+#pragma unroll
+  for (int k = 0; k < kPixPerThread; ++k) {
+    const int i = (blockIdx.x * kPixPerThread + k) * 256 + threadIdx.x;
+    if (i < hw) {
+      const int y = i / W, x = i - y * W;
+      T fx, fy;
+      d2f_pixel(fx, fy, dv[k], x, y, cam, inverse_depth, normalize_flow);
+      fn[i] = fx;
+      fn[hw + i] = fy;
+    }
+  }
 }
 
 template <class T>
@@ -115,7 +147,7 @@ static int depth_to_flow_launch(const T* depth, const T* intrinsics, const T* ro
   DEMON_REQUIRE(n >= 0 && h >= 0 && w >= 0 && n <= 65535, "depth_to_flow: bad size");
   if ((int64_t)n * h * w == 0) return DEMON_OK;
   DEMON_REQUIRE(depth && intrinsics && rotation && translation && flow, "depth_to_flow: null pointer");
-  depth_to_flow_kernel<T><<<dim3(ceil_div(h * w, 256), n), 256, 0, (cudaStream_t)stream>>>(
+  depth_to_flow_kernel<T><<<dim3(ceil_div(h * w, 256 * kPixPerThread), n), 256, 0, (cudaStream_t)stream>>>(
       depth, intrinsics, rotation, translation, flow, h, w, rotation_format, inverse_depth != 0, normalize_flow != 0);
   DEMON_LAUNCH_CHECK();
   return DEMON_OK;
@@ -124,6 +156,7 @@ static int depth_to_flow_launch(const T* depth, const T* intrinsics, const T* ro
 // ---------------------------------------------------------------------------------------------
 // flow_to_depth / flow_to_depth2 (replaces flowtodepth.cc:383-481; the reference has no GPU kernel)
 // ---------------------------------------------------------------------------------------------
+constexpr int kF2DPixPerThread = 4;   // the double-precision camera set-up of thread 0 is shared by 512 pixels
 template <class T>
 __global__ void __launch_bounds__(128) flow_to_depth_kernel(const T* __restrict__ flow, const T* __restrict__ intrinsics,
                                                            const T* __restrict__ rotation, const T* __restrict__ translation,
@@ -136,11 +169,23 @@ __global__ void __launch_bounds__(128) flow_to_depth_kernel(const T* __restrict_
                rotation_format, W, H);
   __syncthreads();
   const int hw = H * W;
-  const int i = blockIdx.x * 128 + threadIdx.x;
-  if (i >= hw) return;
-  const int y = i / W, x = i - y * W;
-  const T* f = flow + (size_t)n * 2 * hw + i;
-  depth[(size_t)n * hw + i] = f2d_pixel(__ldg(f), __ldg(f + hw), x, y, cam, inverse_depth, normalized_flow);
+  const T* f = flow + (size_t)n * 2 * hw;
+  T* dn = depth + (size_t)n * hw;
+  T fx[kF2DPixPerThread], fy[kF2DPixPerThread];
+#pragma unroll
+  for (int k = 0; k < kF2DPixPerThread; ++k) {
+    const int i = (blockIdx.x * kF2DPixPerThread + k) * 128 + threadIdx.x;
+    fx[k] = (i < hw) ? __ldg(f + i) : (T)0;
+    fy[k] = (i < hw) ? __ldg(f + hw + i) : (T)0;
+  }
+#pragma unroll
+  for (int k = 0; k < kF2DPixPerThread; ++k) {
+    const int i = (blockIdx.x * kF2DPixPerThread + k) * 128 + threadIdx.x;
+    if (i < hw) {
+      const int y = i / W, x = i - y * W;
+      dn[i] = f2d_pixel(fx[k], fy[k], x, y, cam, inverse_depth, normalized_flow);
+    }
+  }
 }
 
 template <class T>
@@ -150,7 +195,7 @@ static int flow_to_depth_launch(const T* flow, const T* intrinsics, const T* rot
   DEMON_REQUIRE(n >= 0 && h >= 0 && w >= 0 && n <= 65535, "flow_to_depth: bad size");
   if ((int64_t)n * h * w == 0) return DEMON_OK;
   DEMON_REQUIRE(flow && intrinsics && rotation && translation && depth, "flow_to_depth: null pointer");
-  flow_to_depth_kernel<T><<<dim3(ceil_div(h * w, 128), n), 128, 0, (cudaStream_t)stream>>>(
+  flow_to_depth_kernel<T><<<dim3(ceil_div(h * w, 128 * kF2DPixPerThread), n), 128, 0, (cudaStream_t)stream>>>(
       flow, intrinsics, rotation, translation, depth, h, w, rotation_format, inverse_depth != 0, normalized_flow != 0);
   DEMON_LAUNCH_CHECK();
   return DEMON_OK;

@@ -32,7 +32,11 @@ def main():
     rows = []
     for tag, (n, h, w) in (("1024x768 x8", (8, 768, 1024)), ("64x48 x64", (64, 48, 64)), ("256x192 x64", (64, 192, 256))):
         img = torch.rand(n, 3, h, w, device="cuda") - 0.5
-        disp = (torch.rand(n, 2, h, w, device="cuda") - 0.5) * 0.05
+        # a smooth displacement field (what flow networks produce): low-frequency waves of +-2.5 % of the image size;
+        # `rough` is the adversarial case, an independent random displacement per pixel (every gather misses its neighbours)
+        yy, xx = torch.meshgrid(torch.linspace(0, 6.28, h, device="cuda"), torch.linspace(0, 6.28, w, device="cuda"), indexing="ij")
+        disp = (0.025 * torch.stack([torch.sin(xx + 0.5 * yy), torch.cos(yy - 0.3 * xx)])[None].repeat(n, 1, 1, 1)).contiguous()
+        rough = (torch.rand(n, 2, h, w, device="cuda") - 0.5) * 0.05
         depth = torch.rand(n, 1, h, w, device="cuda") + 0.3
         K = torch.tensor([[0.89115971, 1.18821287, 0.5, 0.5]], device="cuda").repeat(n, 1)
         r = (torch.rand(n, 3, device="cuda") - 0.5) * 0.1
@@ -40,6 +44,7 @@ def main():
         px = n * h * w
         cases = [
             ("warp2d (value, normalized)", lambda: ops.warp2d(img, disp, normalized=True, border_mode="value"), (3 + 2 + 3) * 4 * px),
+            ("warp2d (random displacement per pixel)", lambda: ops.warp2d(img, rough, normalized=True, border_mode="value"), (3 + 2 + 3) * 4 * px),
             ("depth_to_flow", lambda: ops.depth_to_flow(depth, K, r, t, inverse_depth=True, normalize_flow=True), (1 + 2) * 4 * px),
             ("flow_to_depth", lambda: ops.flow_to_depth(disp, K, r, t, normalized_flow=True, inverse_depth=True, nowarning=True), (2 + 1) * 4 * px),
             ("median3x3_downsample", lambda: ops.median3x3_downsample(img), (3 + 0.75) * 4 * px),
