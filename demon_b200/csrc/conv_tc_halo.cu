@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
       for (int t = 0; t < p.ntaps; ++t) { cls_bits |= (uint32_t)p.taps[t].cls << (2 * t); first_bits |= (uint32_t)p.taps[t].first << t; }
       const uint32_t w_lo_off = (uint32_t)p.n_tile * 128u;
       const uint32_t w_ring_addr = smem_u32(w_ring);
-      long long w_cempty = 0, w_tfull = 0;
+      long long w_cempty = 0, w_tfull = 0, w_poll = 0, w_issue = 0, w_commit = 0;
       const long long t_begin = clock64();
       int it = 0;
       bool rdy_t = mbar_try(tfull0, 0);
@@ -258,6 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
         const uint32_t d_base = tmem_base + (uint32_t)(a * acc_cols);
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           for (int t = 0; t < p.ntaps; ++t) {
+            const long long tq0 = timed ? clock64() : 0;
             if (!rdy_t) wait_t(tfull0 + 8 * st, pt, p.err, w_tfull, timed);
             tc_fence_after();
             const uint32_t a_hi = t_ring + (uint32_t)(st * 64), a_lo = a_hi + 32;
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
             if (++st == p.st) { st = 0; pt ^= 1; }
             if (++sw == p.sw) sw = 0;
             rdy_t = mbar_try(tfull0 + 8 * st, pt);   // poll the NEXT step's barrier
+            const long long tq1 = timed ? clock64() : 0;
             const uint64_t w_hi = umma_desc_sw128_sbo(wbase, 1024);
             const uint32_t d_tmem = d_base + ((cls_bits >> (2 * t)) & 3u) * (uint32_t)p.acc_w;
             const bool fresh = (kc == 0) && ((first_bits >> t) & 1u);
@@ -287,15 +289,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
 #pragma unroll
               for (int j = 0; j < 4; ++j) umma_tf32_ts(d_tmem, a_hi + 8 * j, w_hi + (uint64_t)(2 * j), idesc, !(fresh && j == 0));
             }
+            const long long tq2 = timed ? clock64() : 0;
             umma_commit(tempty0 + 8 * st_cur);
             umma_commit(wempty0 + 8 * sw_cur);
             if (kc == p.k_chunks - 1 && t == p.ntaps - 1) umma_commit(cfull0 + 8 * a);
+            if (timed) { const long long tq3 = clock64(); w_poll += tq1 - tq0; w_issue += tq2 - tq1; w_commit += tq3 - tq2; }
           }
         }
       }
       if (timed) {
         long long* tm = p.timing + blockIdx.x * 16;
-        tm[2] = w_cempty; tm[3] = w_tfull; tm[5] = 0; tm[9] = clock64() - t_begin;
+        tm[2] = w_cempty; tm[3] = w_tfull; tm[5] = 0; tm[13] = w_poll; tm[14] = w_issue; tm[15] = w_commit; tm[9] = clock64() - t_begin;
       }
     }
   } else if (warp < 2 + kStagerWarps) {

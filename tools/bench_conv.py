@@ -58,7 +58,7 @@ def main():
         if lib.demon_debug_tc_timing(0, buf.ctypes.data, 148) == 0:
             names = ["A-producer wait A_empty", "W-producer wait W_empty", "MMA wait accum_empty", "MMA wait T_full", "stager0 wait T_empty",
                      "MMA wait W_full", "stager0 wait A_full", "epilogue wait accum_full", "A-producer total", "MMA total", "stager0 total",
-                     "epilogue total", "stager1 wait T_empty", "stager0 split+tcgen05.st issue", "stager0 tcgen05.wait::st+fence"]
+                     "epilogue total", "stager1 wait T_empty", "MMA thread: wait + fence + next poll", "MMA thread: descriptors + 8..12 tcgen05.mma", "MMA thread: commits"]
             m = buf.mean(axis=0)
             for i, nm in enumerate(names):
                 print("  %-28s %12.0f cycles (avg per CTA)" % (nm, m[i]))
