@@ -39,6 +39,8 @@ constexpr int kMaxTStages = 8;
 constexpr int kTileH = 16, kTileW = 8;
 constexpr int kMaxPlanes = 4;
 constexpr int kMaxWStages = 8;
+constexpr int kEpiRowBytes = 144;                  // 32 fp32 + 16 B pad: the epilogue's transpose buffer, conflict free both ways
+constexpr int kEpiStageBytes = 32 * kEpiRowBytes;  // per epilogue warp
 
 struct HaloPlane {
   int c_off;      // coordinate offset in dim 0 (rx * in_pitch)
@@ -405,11 +407,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
     }
   } else if (warp < 2 + kStagerWarps + 4) {
     // ===== epilogue ======================================================================================================
+    // After the TMEM load a thread holds one output pixel (GEMM row) x 32 channels, and consecutive pixels are a whole
+    // pixel pitch apart in global memory: storing rows directly costs 32 memory wavefronts per store instruction, and
+    // the wait counters showed the epilogue (not the MMA thread) bounding the layers with few steps per tile (conv1y,
+    // conv2y: ~3400 / ~9000 cycles per tile).  Each warp therefore transposes its 32 x 32 block through shared memory
+    // (row pitch 144 B: conflict free both ways) and stores with lane = (row % 4, 16-byte chunk), i.e. four pixels x 128
+    // contiguous bytes per instruction; the bias is then one float4 per lane and chunk.
     const int q = warp & 3;
-    const int m = q * 32 + lane;
-    const int xl = PER_TAP ? (m % p.tw) : (m & 7);
-    const int yl = PER_TAP ? ((m / p.tw) % p.th) : (m >> 3);
-    const int nl = PER_TAP ? (m / (p.tw * p.th)) : 0;
+    const int sub = lane >> 3, chunk = lane & 7;
+    const uint32_t stg = smem_u32(w_ring + (size_t)p.sw * p.w_stage_bytes) + (uint32_t)(q * kEpiStageBytes);
+    int rowoff[8];          // element offset of row 4 i + sub of this warp's block inside the output tile
+    uint32_t rowpos[8];     // its (yl, xl, nl) for the bounds test
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = q * 32 + 4 * i + sub;
+      const int xl = PER_TAP ? (m % p.tw) : (m & 7);
+      const int yl = PER_TAP ? ((m / p.tw) % p.th) : (m >> 3);
+      const int nl = PER_TAP ? (m / (p.tw * p.th)) : 0;
+      rowoff[i] = ((nl * p.Hfull + yl * p.osy) * p.Wfull + xl * p.osx) * p.out_pitch;
+      rowpos[i] = (uint32_t)yl | ((uint32_t)xl << 10) | ((uint32_t)nl << 20);
+    }
     long long w_cfull = 0;
     const long long t_begin = clock64();
     int it = 0;
@@ -420,12 +437,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
       wait_t(cfull0 + 8 * a, (p.nbuf == 2) ? ((it >> 1) & 1) : (it & 1), p.err, w_cfull, timed);
       __syncwarp();
       tc_fence_after();
-      const int oy = y0 + yl, ox = x0 + xl;
-      n += nl;
-      const bool valid = oy < p.Ho && ox < p.Wo && n < p.B;
+      uint32_t rowmask = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int yl = (int)(rowpos[i] & 1023u), xl = (int)((rowpos[i] >> 10) & 1023u), nl = (int)(rowpos[i] >> 20);
+        if (y0 + yl < p.Ho && x0 + xl < p.Wo && n + nl < p.B) rowmask |= 1u << i;
+      }
+      float* tile_out = p.out + ((size_t)(n * p.Hfull + y0 * p.osy) * p.Wfull + x0 * p.osx) * p.out_pitch;
       const int cbase = nt * p.n_tile;
       for (int cls = 0; cls < p.nclass; ++cls) {
-        float* orow = p.out + ((size_t)(n * p.Hfull + oy * p.osy + p.cls_ooy[cls]) * p.Wfull + ox * p.osx + p.cls_oox[cls]) * p.out_pitch;
+        float* cls_out = tile_out + (size_t)(p.cls_ooy[cls] * p.Wfull + p.cls_oox[cls]) * p.out_pitch;
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * acc_cols + cls * p.acc_w);
         for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
           uint32_t v[32];
@@ -439,23 +460,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
             for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
           }
           tmem_ld_wait();
-          if (valid) {
+          __syncwarp();   // the previous block has been read back
 #pragma unroll
-            for (int gq = 0; gq < 8; ++gq) {
-              const int col = cbase + c0 + 4 * gq;
-              if (4 * gq < ncol && col < p.Cout) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                float4 o;
-                o.x = __uint_as_float(v[4 * gq + 0]) + b.x;
-                o.y = __uint_as_float(v[4 * gq + 1]) + b.y;
-                o.z = __uint_as_float(v[4 * gq + 2]) + b.z;
-                o.w = __uint_as_float(v[4 * gq + 3]) + b.w;
-                if (p.leaky) {
-                  o.x = fmaxf(0.1f * o.x, o.x); o.y = fmaxf(0.1f * o.y, o.y);
-                  o.z = fmaxf(0.1f * o.z, o.z); o.w = fmaxf(0.1f * o.w, o.w);
-                }
-                *reinterpret_cast<float4*>(orow + col) = o;
+          for (int c = 0; c < 8; ++c)
+            if (4 * c < ncol)
+              sts128(stg + (uint32_t)(lane * kEpiRowBytes + c * 16),
+                     make_float4(__uint_as_float(v[4 * c + 0]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]),
+                                 __uint_as_float(v[4 * c + 3])));
+          __syncwarp();
+          const int col = cbase + c0 + 4 * chunk;
+          if (4 * chunk < ncol && col < p.Cout) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (!((rowmask >> i) & 1u)) continue;
+              const float4 x = lds128(stg + (uint32_t)((4 * i + sub) * kEpiRowBytes + chunk * 16));
+              float4 o;
+              o.x = x.x + b.x; o.y = x.y + b.y; o.z = x.z + b.z; o.w = x.w + b.w;
+              if (p.leaky) {
+                o.x = fmaxf(0.1f * o.x, o.x); o.y = fmaxf(0.1f * o.y, o.y);
+                o.z = fmaxf(0.1f * o.z, o.z); o.w = fmaxf(0.1f * o.w, o.w);
               }
+              *reinterpret_cast<float4*>(cls_out + rowoff[i] + col) = o;
             }
           }
         }
@@ -613,13 +639,13 @@ static bool halo_build(const ConvProblem* probs, int nclass, int n_tile_req, int
   const int slot = (nsplit == 3) ? n_tile * 256 : (n_tile * 128 + 1023) / 1024 * 1024;
   prm.w_stage_bytes = slot;
   // shared memory: up to 4 halo stages (at least 2), the rest for the weight ring
-  const int budget = 224 * 1024;
+  const int budget = 224 * 1024 - 4 * kEpiStageBytes;   // minus the epilogue's transpose buffers
   prm.sa = kMaxAStages;
   while (prm.sa > 2 && budget - prm.sa * prm.a_region_bytes < 4 * slot) --prm.sa;
   const int rest = budget - prm.sa * prm.a_region_bytes;
   if (rest < 2 * slot) return false;
   prm.sw = std::min(std::min(kMaxWStages, prm.st), rest / slot);   // sw <= st, see the W producer
-  plan.smem_bytes = prm.sa * prm.a_region_bytes + prm.sw * slot + 1024;
+  plan.smem_bytes = prm.sa * prm.a_region_bytes + prm.sw * slot + 4 * kEpiStageBytes + 1024;
   prm.B = p.B;
   prm.total_tiles = m_tiles * prm.n_tiles;
   prm.out = p.out; prm.out_pitch = p.out_pitch; prm.Ho = p.Ho; prm.Wo = p.Wo; prm.Hfull = p.Hfull; prm.Wfull = p.Wfull;

@@ -16,7 +16,9 @@ SHAPES = {
     "refine_conv1_1": ("conv", 64, 96, 128, 64, 64, 3, 3, 1, 1),
     "refine_conv2_1": ("conv", 64, 48, 64, 128, 128, 3, 3, 1, 1),
     "refine0_upconv": ("deconv", 64, 96, 128, 128, 32),
+    "conv1y": ("conv", 64, 192, 256, 8, 32, 9, 1, 2, 1),
     "conv1x": ("conv", 64, 96, 256, 32, 32, 1, 9, 1, 2),
+    "conv2y": ("conv", 64, 96, 128, 32, 64, 7, 1, 2, 1),
     "predict2_conv1": ("conv", 64, 48, 64, 128, 24, 3, 3, 1, 1),
     "conv5_1y": ("conv", 64, 6, 8, 512, 512, 3, 1, 1, 1),
     "conv3x": ("conv", 64, 24, 64, 128, 128, 1, 5, 1, 2),
