@@ -60,6 +60,7 @@ struct HaloTap {
 
 struct HaloParams {
   int tiles_x, tiles_y, B, n_tiles, total_tiles;
+  uint32_t mul_n_tiles, mul_tiles_x, mul_tiles_y;   // fast_div multipliers
   int k_chunks, nplanes, ntaps, nclass;
   // per-tap mode (layers whose images are not made of whole 16x8 tiles): the A stage is ONE tap's 128-pixel tile
   // (tb images x th rows x tw columns, one TMA box per (chunk, tap) step, box coordinates carry the tap like in conv_tc.cu)
@@ -110,14 +111,18 @@ __device__ __forceinline__ void wait_t(uint32_t bar, uint32_t parity, int* err, 
   acc += clock64() - t0;
 }
 
+// x / d for small d by one multiply (mul = 2^32 / d + 1, exact while x * d < 2^32; d == 1 -> mul = 0): the tile decode
+// runs once per tile in four roles, and integer division costs ~25 instructions on a thread that has few to spare
+__device__ __forceinline__ int fast_div(int x, int d, uint32_t mul) { return mul ? (int)__umulhi((uint32_t)x, mul) : x; }
+
 template <bool PER_TAP>
 __device__ __forceinline__ void halo_decode_tile(const HaloParams& p, int tile, int& nt, int& n, int& y0, int& x0) {
-  nt = tile % p.n_tiles;
-  int m = tile / p.n_tiles;
-  const int xb = m % p.tiles_x;
-  m /= p.tiles_x;
-  const int yb = m % p.tiles_y;
-  n = m / p.tiles_y;
+  int m = fast_div(tile, p.n_tiles, p.mul_n_tiles);
+  nt = tile - m * p.n_tiles;
+  const int m1 = fast_div(m, p.tiles_x, p.mul_tiles_x);
+  const int xb = m - m1 * p.tiles_x;
+  n = fast_div(m1, p.tiles_y, p.mul_tiles_y);
+  const int yb = m1 - n * p.tiles_y;
   if (PER_TAP) { n *= p.tb; y0 = yb * p.th; x0 = xb * p.tw; }
   else { y0 = yb * kTileH; x0 = xb * kTileW; }
 }
@@ -217,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
       uint32_t pw = 0;
       long long w_wempty = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles;
+        const int nt = tile - fast_div(tile, p.n_tiles, p.mul_n_tiles) * p.n_tiles;
         const unsigned char* wsrc = p.w + (size_t)nt * steps_per_tile * p.w_stage_bytes;
         for (int kt = 0; kt < steps_per_tile; ++kt) {
           wait_t(wempty0 + 8 * sw, pw ^ 1, p.err, w_wempty, timed);
@@ -427,6 +432,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
       rowoff[i] = ((nl * p.Hfull + yl * p.osy) * p.Wfull + xl * p.osx) * p.out_pitch;
       rowpos[i] = (uint32_t)yl | ((uint32_t)xl << 10) | ((uint32_t)nl << 20);
     }
+    const float slope = p.leaky ? 0.1f : 1.0f;
     long long w_cfull = 0;
     const long long t_begin = clock64();
     int it = 0;
@@ -437,11 +443,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
       wait_t(cfull0 + 8 * a, (p.nbuf == 2) ? ((it >> 1) & 1) : (it & 1), p.err, w_cfull, timed);
       __syncwarp();
       tc_fence_after();
-      uint32_t rowmask = 0;
+      uint32_t rowmask = 0xFFu;
+      const bool whole = PER_TAP ? (y0 + p.th <= p.Ho && x0 + p.tw <= p.Wo && n + p.tb <= p.B) : (y0 + kTileH <= p.Ho && x0 + kTileW <= p.Wo);
+      if (!whole) {
+        rowmask = 0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int yl = (int)(rowpos[i] & 1023u), xl = (int)((rowpos[i] >> 10) & 1023u), nl = (int)(rowpos[i] >> 20);
-        if (y0 + yl < p.Ho && x0 + xl < p.Wo && n + nl < p.B) rowmask |= 1u << i;
+        for (int i = 0; i < 8; ++i) {
+          const int yl = (int)(rowpos[i] & 1023u), xl = (int)((rowpos[i] >> 10) & 1023u), nl = (int)(rowpos[i] >> 20);
+          if (y0 + yl < p.Ho && x0 + xl < p.Wo && n + nl < p.B) rowmask |= 1u << i;
+        }
       }
       float* tile_out = p.out + ((size_t)(n * p.Hfull + y0 * p.osy) * p.Wfull + x0 * p.osx) * p.out_pitch;
       const int cbase = nt * p.n_tile;
@@ -460,6 +470,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
             for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
           }
           tmem_ld_wait();
+          if (cls == p.nclass - 1 && c0 + 32 >= p.n_tile) {   // last TMEM read of the tile: hand the accumulators back now
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(cempty0 + 8 * a);
+          }
           __syncwarp();   // the previous block has been read back
 #pragma unroll
           for (int c = 0; c < 8; ++c)
@@ -471,24 +486,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
           const int col = cbase + c0 + 4 * chunk;
           if (4 * chunk < ncol && col < p.Cout) {
             const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            float* colp = cls_out + col;
+            const uint32_t sbase = stg + (uint32_t)(sub * kEpiRowBytes + chunk * 16);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               if (!((rowmask >> i) & 1u)) continue;
-              const float4 x = lds128(stg + (uint32_t)((4 * i + sub) * kEpiRowBytes + chunk * 16));
+              const float4 x = lds128(sbase + (uint32_t)(4 * i * kEpiRowBytes));
               float4 o;
               o.x = x.x + b.x; o.y = x.y + b.y; o.z = x.z + b.z; o.w = x.w + b.w;
-              if (p.leaky) {
-                o.x = fmaxf(0.1f * o.x, o.x); o.y = fmaxf(0.1f * o.y, o.y);
-                o.z = fmaxf(0.1f * o.z, o.z); o.w = fmaxf(0.1f * o.w, o.w);
-              }
-              *reinterpret_cast<float4*>(cls_out + rowoff[i] + col) = o;
+              // max(slope * x, x) with slope 0.1 (leaky ReLU, helpers.py:36-38) or 1 (identity, exact)
+              o.x = fmaxf(slope * o.x, o.x); o.y = fmaxf(slope * o.y, o.y);
+              o.z = fmaxf(slope * o.z, o.z); o.w = fmaxf(slope * o.w, o.w);
+              *reinterpret_cast<float4*>(colp + rowoff[i]) = o;
             }
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(cempty0 + 8 * a);
     }
     if (timed && q == 0 && lane == 0) { p.timing[blockIdx.x * 16 + 7] = w_cfull; p.timing[blockIdx.x * 16 + 11] = clock64() - t_begin; }
   }
@@ -648,6 +661,9 @@ static bool halo_build(const ConvProblem* probs, int nclass, int n_tile_req, int
   plan.smem_bytes = prm.sa * prm.a_region_bytes + prm.sw * slot + 4 * kEpiStageBytes + 1024;
   prm.B = p.B;
   prm.total_tiles = m_tiles * prm.n_tiles;
+  auto fd = [](int d) { return d <= 1 ? 0u : (uint32_t)((1ull << 32) / (uint64_t)d + 1ull); };
+  prm.mul_n_tiles = fd(prm.n_tiles); prm.mul_tiles_x = fd(prm.tiles_x); prm.mul_tiles_y = fd(prm.tiles_y);
+  if ((uint64_t)prm.total_tiles * (uint64_t)std::max(prm.n_tiles, std::max(prm.tiles_x, prm.tiles_y)) >= (1ull << 32)) return false;
   prm.out = p.out; prm.out_pitch = p.out_pitch; prm.Ho = p.Ho; prm.Wo = p.Wo; prm.Hfull = p.Hfull; prm.Wfull = p.Wfull;
   prm.osy = p.osy; prm.osx = p.osx; prm.Cout = p.Cout; prm.bias = p.bias; prm.leaky = p.leaky;
   for (int c = 0; c < nclass; ++c) { prm.cls_ooy[c] = probs[c].ooy; prm.cls_oox[c] = probs[c].oox; }
