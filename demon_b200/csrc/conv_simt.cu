@@ -6,6 +6,8 @@
 // 256 threads, a BM x BN output tile (BM*BN = 4096), 4x4 outputs per thread, BK = 16, the A tile
 // gathered on the fly from the NHWC input (zero for padding taps), global loads of tile k+1 in flight
 // while tile k is multiplied out of shared memory.
+#include <cstdlib>
+
 #include "conv.cuh"
 
 namespace demon {
@@ -165,12 +167,85 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvProblem p) {
   }
 }
 
-// Direct convolution for the prediction heads' last layers (Cout <= 4, Cin <= 32, e.g. 24 -> 4 and 16 -> 1, 3x3): one thread
-// per output pixel, weights in shared memory, the taps' pixels come through L1 (every input pixel is read by up to 9
-// neighbouring threads of the same CTA row).  These layers have ~150 MACs per pixel: the implicit-GEMM tile machinery
-// above costs more than the arithmetic.  grid (ceil(Wo/128), Ho, B).
-template <int COUT>
+// Direct convolution for the prediction heads' last layers (Cout <= 4, Cin <= 32, e.g. 24 -> 4 and 16 -> 1, 3x3).  These
+// layers have ~150 MACs per pixel and are bound by reading their input (64-128 B per pixel): LPP lanes share one output
+// pixel, each owning a float4 of its channels, so that a warp load covers 32 / LPP adjacent pixels = 512 contiguous bytes
+// (one thread per pixel touched 16 B of every 64-B pixel per instruction and ran at a tenth of the HBM rate); the taps'
+// re-reads hit L1; the LPP partial sums are combined by shuffles in a fixed order.  Weights sit in shared memory.
+// grid (ceil(Wo / (8 * 128 / LPP)), Ho, B).
+constexpr int kSmallCoutGroups = 4;
+template <int COUT, int LPP, int NT>   // NT: compile-time tap count (9 = 3x3) or 0 = run-time loop
 __global__ void __launch_bounds__(128) conv_small_cout_kernel(const ConvProblem p) {
+  __shared__ __align__(16) float ws[kMaxTaps * 32 * COUT];
+  const int nw = p.ntaps * p.Cin;
+  for (int i = threadIdx.x; i < nw * COUT; i += 128) {
+    const int k = i / COUT, co = i - k * COUT;
+    ws[i] = (co < p.Cout) ? __ldg(p.w + (size_t)k * p.Cout_pad + co) : 0.f;
+  }
+  __syncthreads();
+  constexpr int PPB = 128 / LPP;
+  const int pix = threadIdx.x / LPP, chunk = threadIdx.x % LPP;
+  const int oy = blockIdx.y, n = blockIdx.z;
+  for (int g = 0; g < kSmallCoutGroups; ++g) {   // the CTA's weights serve kSmallCoutGroups x PPB pixels of the row
+    const int ox = (blockIdx.x * kSmallCoutGroups + g) * PPB + pix;
+    const bool active = ox < p.Wo && chunk * 4 < p.Cin;
+    float acc[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+    if (active && NT > 0) {
+      // all taps' loads in flight before the first FMA (a tap outside the image contributes 0 * w)
+      float4 v[NT > 0 ? NT : 1];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int iy = oy * p.sy + p.dy[t], ix = ox * p.sx + p.dx[t];
+        v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (iy >= 0 && iy < p.Hi && ix >= 0 && ix < p.Wi)
+          v[t] = __ldg(reinterpret_cast<const float4*>(p.in + ((size_t)(n * p.Hi + iy) * p.Wi + ix) * p.in_pitch) + chunk);
+      }
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const float* wt = ws + (size_t)(t * p.Cin + chunk * 4) * COUT;
+        const float vv[4] = {v[t].x, v[t].y, v[t].z, v[t].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) acc[c] = fmaf(vv[j], wt[j * COUT + c], acc[c]);
+      }
+    } else if (active) {
+      for (int t = 0; t < p.ntaps; ++t) {
+        const int iy = oy * p.sy + p.dy[t], ix = ox * p.sx + p.dx[t];
+        if (iy < 0 || iy >= p.Hi || ix < 0 || ix >= p.Wi) continue;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p.in + ((size_t)(n * p.Hi + iy) * p.Wi + ix) * p.in_pitch) + chunk);
+        const float* wt = ws + (size_t)(t * p.Cin + chunk * 4) * COUT;
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) acc[c] = fmaf(vv[j], wt[j * COUT + c], acc[c]);
+      }
+    }
+#pragma unroll
+    for (int off = LPP / 2; off >= 1; off >>= 1)
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], off);
+    if (chunk != 0 || ox >= p.Wo) continue;
+    float* o = p.out + ((size_t)(n * p.Hfull + oy * p.osy + p.ooy) * p.Wfull + ox * p.osx + p.oox) * p.out_pitch;
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) {
+      if (c < p.Cout) {
+        float x = acc[c] + __ldg(p.bias + c);
+        if (p.leaky) x = fmaxf(0.1f * x, x);
+        if (c == 0 && p.scale != nullptr) x *= __ldg(p.scale + (size_t)n * p.scale_stride);
+        o[c] = x;
+      }
+    }
+  }
+}
+
+// One thread per output pixel: faster than lane sharing for the 24 -> 4 heads at 48x64 (0.036 vs 0.10 ms at batch 64, the
+// shuffles and the 6-of-8 active lanes cost more than the uncoalesced loads), slower for 16 -> 1 at 192x256 (0.27 vs 0.16 ms)
+template <int COUT>
+__global__ void __launch_bounds__(128) conv_small_cout_pixel_kernel(const ConvProblem p) {
   __shared__ float ws[kMaxTaps * 32 * COUT];
   const int nw = p.ntaps * p.Cin;
   for (int i = threadIdx.x; i < nw * COUT; i += 128) {
@@ -233,9 +308,21 @@ int conv_simt_launch(const ConvProblem& p, cudaStream_t stream) {
   DEMON_REQUIRE(M < (1ll << 31), "conv: too many output pixels");
   if (M == 0 || p.Cout == 0) return DEMON_OK;
   if (p.Cout <= 4 && p.Cin <= 32 && p.ntaps > 1 && p.partial == nullptr && p.Ho <= 65535 && p.B <= 65535) {
-    dim3 grid(ceil_div(p.Wo, 128), p.Ho, p.B);
-    if (p.Cout == 1) conv_small_cout_kernel<1><<<grid, 128, 0, stream>>>(p);
-    else conv_small_cout_kernel<4><<<grid, 128, 0, stream>>>(p);
+    static const int pixel_mode = []() { const char* e = getenv("DEMON_SMALL_COUT_PIXEL"); return e ? atoi(e) : 2; }();   // 0: lane sharing everywhere, 1: pixel kernel everywhere, 2 (default, measured): lane sharing for Cout == 1 only
+    if (pixel_mode == 1 || (pixel_mode == 2 && p.Cout > 1)) {
+      dim3 g1(ceil_div(p.Wo, 128), p.Ho, p.B);
+      if (p.Cout == 1) conv_small_cout_pixel_kernel<1><<<g1, 128, 0, stream>>>(p);
+      else conv_small_cout_pixel_kernel<4><<<g1, 128, 0, stream>>>(p);
+      DEMON_LAUNCH_CHECK();
+      return DEMON_OK;
+    }
+    const int lpp = (p.Cin <= 16) ? 4 : 8;   // lanes per output pixel, one float4 of channels each
+    dim3 grid(ceil_div(p.Wo, (128 / lpp) * kSmallCoutGroups), p.Ho, p.B);
+    const bool nine = p.ntaps == 9;
+    if (p.Cout == 1 && lpp == 4) { if (nine) conv_small_cout_kernel<1, 4, 9><<<grid, 128, 0, stream>>>(p); else conv_small_cout_kernel<1, 4, 0><<<grid, 128, 0, stream>>>(p); }
+    else if (p.Cout == 1) { if (nine) conv_small_cout_kernel<1, 8, 9><<<grid, 128, 0, stream>>>(p); else conv_small_cout_kernel<1, 8, 0><<<grid, 128, 0, stream>>>(p); }
+    else if (lpp == 4) { if (nine) conv_small_cout_kernel<4, 4, 9><<<grid, 128, 0, stream>>>(p); else conv_small_cout_kernel<4, 4, 0><<<grid, 128, 0, stream>>>(p); }
+    else { if (nine) conv_small_cout_kernel<4, 8, 9><<<grid, 128, 0, stream>>>(p); else conv_small_cout_kernel<4, 8, 0><<<grid, 128, 0, stream>>>(p); }
     DEMON_LAUNCH_CHECK();
     return DEMON_OK;
   }
