@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--precision", default=None, choices=["fp32", "3xtf32", "tf32"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="pairs per GPU (default: BASELINE.json configs[2])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=2, help="batches in flight per GPU (pipelines on their own streams)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     graph_warmup = 2 * N_INPUT_SETS + 1     # every rotating input set must be seen twice before its CUDA graph replays
@@ -234,15 +235,16 @@ def main():
     # Two batches in flight per GPU: a second pipeline (own workspace, own output buffers) on a second stream, steps
     # alternate between the two.  The kernels of one batch fill the SMs the other leaves idle (tails of the persistent
     # kernels, the low-resolution layers, the dense layers); every step is still one full batch through the whole path.
-    pipes = [pipe, DemonPipeline(sess, batch_size=B, iterations=ITERATIONS, private_net=True)]
-    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
-    outs2 = [outs, {k: torch.empty_like(v) for k, v in outs.items()}]
-    gathers = [gather, parallel.OutputGather(B, world, device=dev)]
+    NF = max(1, args.inflight)
+    pipes = [pipe] + [DemonPipeline(sess, batch_size=B, iterations=ITERATIONS, private_net=True) for _ in range(NF - 1)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(NF)]
+    outs2 = [outs] + [{k: torch.empty_like(v) for k, v in outs.items()} for _ in range(NF - 1)]
+    gathers = [gather] + [parallel.OutputGather(B, world, device=dev) for _ in range(NF - 1)]
 
     def step2(i):
-        k = i % 2
+        k = i % NF
         with torch.cuda.stream(streams[k]):
-            pipes[k].forward(inputs[(i // 2) % N_INPUT_SETS], None, outs2[k])
+            pipes[k].forward(inputs[(i // NF) % N_INPUT_SETS], None, outs2[k])
             gathers[k](outs2[k]["predict_depth0"], outs2[k]["predict_rotation"], outs2[k]["predict_translation"])
 
     def barrier():
@@ -254,7 +256,7 @@ def main():
     # Two timed regions: the first gives `value` (no instrumentation, two batches in flight); the second runs the same
     # steps on one stream with CUDA events around every layer launch on the launching stream (demon_net_profile_*) and
     # feeds the roofline figures.
-    for i in range(2 * max(args.warmup, graph_warmup)):
+    for i in range(NF * max(args.warmup, graph_warmup)):
         step2(i)
     for i in range(args.warmup):
         step(i)
@@ -266,12 +268,14 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(streams[0])
-    streams[1].wait_event(ev0)
+    for k in range(1, NF):
+        streams[k].wait_event(ev0)
     for i in range(args.steps):
         step2(i)
-    ev_b = torch.cuda.Event()
-    ev_b.record(streams[1])
-    streams[0].wait_event(ev_b)
+    for k in range(1, NF):
+        ev_b = torch.cuda.Event()
+        ev_b.record(streams[k])
+        streams[0].wait_event(ev_b)
     ev1.record(streams[0])
     barrier()
     ms_value = ev0.elapsed_time(ev1)
@@ -349,18 +353,19 @@ def main():
     # timed region ends when the last result is on the host.
     e2e = None
     if True:
-        h_in = [synthetic_inputs(B, 4321 + rank + 1000 * i).pin_memory() for i in range(2)]
-        h_depth = [torch.empty(B, 1, 192, 256).pin_memory() for _ in range(2)]
-        h_rot = [torch.empty(B, 3).pin_memory() for _ in range(2)]
-        h_tr = [torch.empty(B, 3).pin_memory() for _ in range(2)]
+        NE = max(2, NF) if NF > 1 else 1
+        h_in = [synthetic_inputs(B, 4321 + rank + 1000 * i).pin_memory() for i in range(NE)]
+        h_depth = [torch.empty(B, 1, 192, 256).pin_memory() for _ in range(NE)]
+        h_rot = [torch.empty(B, 3).pin_memory() for _ in range(NE)]
+        h_tr = [torch.empty(B, 3).pin_memory() for _ in range(NE)]
         e2e_steps = max(4, min(args.steps, 20))
 
         def e2e_step(i):
-            k = i % 2
+            k = i % NE
             streams[k].synchronize()            # the previous result of this slot is on the host (and may be consumed)
             pipes[k].forward_host_async(h_in[k], None, h_depth[k], h_rot[k], h_tr[k], streams[k])
 
-        for i in range(6):
+        for i in range(3 * NE):
             e2e_step(i)
         torch.cuda.synchronize()
         barrier()
@@ -394,7 +399,7 @@ def main():
                            "l2": "%d rotating input batches of %.1f MB (> 126 MB L2) and a %.2f GB activation workspace rewritten every step"
                                  % (N_INPUT_SETS, B * 6 * 192 * 256 * 4 / 1e6, lib.demon_net_workspace_bytes(net.ptr) / 1e9),
                            "parallelism": "dp%d, one NCCL all-gather of depth0+motion per step" % world if world > 1 else "single GPU",
-                           "batches_in_flight": "2 per GPU (two pipelines with own workspaces on two CUDA streams, steps alternate); the "
+                           "batches_in_flight": "%d per GPU (pipelines with own workspaces on their own CUDA streams, steps alternate); the " % NF +
                                                 "instrumented region behind `roofline` runs the same steps on one stream",
                            "flops_per_pair": 2.0 * W.macs_per_pair()["pipeline"]},
                 "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
