@@ -5,19 +5,28 @@
 // first and last layers that makes the kernel L2-bandwidth bound.  Here the output tile is 16 rows x 8 columns and,
 // per 32-channel chunk, ONE TMA box per stride-parity plane brings the tile plus its halo into shared memory
 // ((16+nqy-1) x (8+nqx-1) pixels, 128 bytes per pixel, 128-byte swizzle).  Every tap is then just a different START
-// ADDRESS of the same shared-memory image:
+// ADDRESS inside the same shared-memory image:
 //
-//     MMA row m = (y, x) of the tile  ->  halo pixel (y + qy - qy_min, x + qx - qx_min)
-//     descriptor start = plane + ((qy - qy_min) * cols + (qx - qx_min)) * 128,   stride byte offset = cols * 128
+//     GEMM row m = (y, x) of the tile  ->  halo pixel (y + qy - qy_min, x + qx - qx_min)
 //
-// which works because the tensor core applies the 128-byte swizzle on ABSOLUTE shared-memory address bits: a start
-// address shifted by whole 128-byte rows and a stride that is not a multiple of 1024 read exactly the expected rows
-// (measured with tools/umma_shift_probe.cu; the descriptor's base_offset field must stay 0).  The 8 rows of a swizzle
-// atom are 8 horizontally adjacent pixels, the 16 atoms of an M = 128 operand are the 16 tile rows.
+// Warp roles (15 warps, persistent over tiles, mbarrier rings between them, every wait bounded):
+//     warp 0        A producer: the halo boxes (TMA)
+//     warp 14       W producer: one pre-swizzled [W_hi ; W_lo] block per (chunk, tap) step (cp.async.bulk); its bytes complete
+//                   on the step's barrier
+//     warps 2..9    stagers, two groups of four alternating steps: shifted pixel rows of the halo image -> registers ->
+//                   A_hi (raw fp32) and A_lo = A - trunc_tf32(A) in a TMEM ring slot (tcgen05.st)
+//     warp 1        MMA thread: TS-mode tcgen05.mma kind::tf32 (A from TMEM, B = weights from shared memory), 3xTF32 as two
+//                   stacked instructions for N <= 64, one poll and two commits per step
+//     warps 10..13  epilogue: tcgen05.ld -> transpose through shared memory -> bias, leaky ReLU -> coalesced NHWC stores
 //
-// Weights stream through their own ring, one block per (chunk, tap); all sub-pixel classes of a transposed convolution
-// accumulate side by side in TMEM (nclass x N columns, double buffered), so the input halo is shared by all 16 taps.
-// Everything else (3xTF32 split by the splitter warps, persistent tiles, warp roles, bounded waits) is as in conv_tc.cu.
+// (The first version of this kernel fed the tap-shifted halo rows to the tensor core directly from shared memory -- a
+// descriptor start shifted by whole 128-byte rows and a stride that is not a multiple of 1024 read exactly the expected
+// rows, because the 128-byte swizzle is applied on ABSOLUTE shared-memory address bits, tools/umma_shift_probe.cu --
+// but a shared-memory A operand costs ~43 cycles per instruction on top of N/2, tools/umma_rate_probe.cu.)
+//
+// All sub-pixel classes of a transposed convolution accumulate side by side in TMEM (nclass x N columns, double
+// buffered when they fit), so the input halo is shared by all 16 taps.  Variants: PER_TAP (images that are not made of
+// whole 16 x 8 tiles: one 128-pixel box per step instead of a halo) and CIN8 (8-channel inputs: four taps per K = 32 step).
 #include <cuda.h>
 
 #include <algorithm>
