@@ -80,6 +80,10 @@ SIMT_CASES = [
     (1, 16, 20, 4, 32, 3, 3, 1, 1),     # netRefine/conv0
     (1, 16, 20, 32, 64, 3, 3, 2, 2),    # netRefine/conv1
     (1, 10, 12, 16, 1, 3, 3, 1, 1),     # predict_depth0/conv2
+    (2, 9, 150, 16, 1, 3, 3, 1, 1),     # same head, several pixel groups per CTA and a ragged last one
+    (1, 7, 37, 32, 1, 3, 3, 1, 1),      # eight lanes per pixel
+    (1, 8, 20, 16, 1, 3, 1, 1, 1),      # run-time tap loop of the lane-sharing kernel
+    (2, 5, 70, 24, 4, 3, 3, 1, 1),      # 24 -> 4 head, wider than one CTA
     (5, 1, 1, 256, 7, 1, 1, 1, 1),      # dense as 1x1 conv
 ]
 
