@@ -10,10 +10,11 @@ GPUs) at N=8 -- weak scaling, pairs are independent, the only collective is one 
 depth / motion tensors, inside the timed region.
 
 One JSON line on stdout (rank 0):
-  value        pairs/s, inputs resident in HBM, whole job
-  e2e          pairs/s through the C-ABI host-buffer entry (pinned host -> device -> pipeline -> host)
+  value        pairs/s, inputs resident in HBM, whole job; `--inflight` (default 2) batches per GPU are in flight on their
+               own streams and pipelines (every step is still one full batch through the whole path)
+  e2e          pairs/s through the C-ABI host-buffer entry (pinned host -> device -> pipeline -> host), same scheme
   roofline     the dominant kernel (the tcgen05 conv kernel; the fp32 SIMT conv kernel when the net runs in
-               fp32 mode) timed with CUDA events around its launches inside the timed region
+               fp32 mode) timed with CUDA events around its launches in a second, single-stream timed region
   cpu_baseline the CPU oracle (torch-CPU fp32 + C geometry ops) on a bounded sample, host cores stated
 `--impl reference` times that CPU path alone (TensorFlow 1.4 cannot be installed here).
 """
