@@ -43,9 +43,13 @@ N_INPUT_SETS = 4     # rotating input batches: 4 x 75.5 MB > 126 MB L2 (plus a ~
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
-        p = json.load(open(path))
-        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
-                "source": "measured"}
+        try:
+            p = json.load(open(path))
+            burst = float(p.get("bf16_tflops", 1590.0))
+            return {"hbm_gbs": float(p.get("hbm_gbs", 6650.0)), "bf16_tflops": burst,
+                    "bf16_tflops_sustained": float(p.get("bf16_tflops_sustained", burst)), "source": "measured"}
+        except (OSError, ValueError, TypeError):
+            pass
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
