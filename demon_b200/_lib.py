@@ -50,6 +50,9 @@ PROTOTYPES = {
     "demon_net_layer_name": [_P, c_int],
     "demon_net_layer_profile": [_P, c_int, _P, _P, _P, _P],
     "demon_debug_tc_timeouts": [],
+    "demon_check_errors": [],
+    "demon_debug_describe_layers": [_P, _P, c_int],
+    "demon_debug_describe_conv": [c_int] * 13 + [_P, c_int],
     "demon_debug_tc_timing": [c_int, _P, c_int],
     "demon_conv2d_nhwc": [_P, _P] + [c_int] * 9 + [_P, _P, c_int, c_int, _P],
     "demon_deconv4x4s2_nhwc": [_P, _P] + [c_int] * 5 + [_P, _P, c_int, c_int, _P],
@@ -90,6 +93,12 @@ def load():
             fn.restype = _RESTYPES.get(name, c_int)
         _lib = lib
     return _lib
+
+
+def check_errors():
+    """Synchronise the current device and raise if a tcgen05 kernel's bounded pipeline wait timed out since the last
+    check (its outputs are garbage) or a CUDA error is pending.  Cheap enough to call once per batch."""
+    check(load().demon_check_errors())
 
 
 def check(rc):

@@ -19,6 +19,7 @@
 #include <cuda.h>
 
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "conv_tc.cuh"
@@ -305,16 +306,7 @@ Tiling choose_tiling(int B, int Ho, int Wo) {
   return best;
 }
 
-int num_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
-  return sms;
-}
+int num_sms() { return tc_device_state().sms; }
 
 }  // namespace
 
@@ -410,13 +402,25 @@ void tc_layer_free(TcLayer& t) {
   t.w_packed = nullptr;
 }
 
-int* tc_error_flag() {
-  static int* flag = nullptr;
-  if (!flag) {
-    cudaMalloc(&flag, sizeof(int));
-    cudaMemset(flag, 0, sizeof(int));
+TcDeviceState& tc_device_state() {
+  constexpr int kMaxDevices = 64;
+  static TcDeviceState states[kMaxDevices];
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) dev = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  TcDeviceState& s = states[dev];
+  if (s.device != dev) {
+    s = TcDeviceState();
+    s.device = dev;
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    s.sms = sms > 0 ? sms : 148;
+    if (cudaMalloc(&s.err_dev, sizeof(int)) == cudaSuccess) cudaMemset(s.err_dev, 0, sizeof(int));
+    else s.err_dev = nullptr;
   }
-  return flag;
+  return s;
 }
 
 int conv_tc_launch(const TcLayer& t, const ConvProblem* probs, cudaStream_t stream) {
@@ -448,11 +452,12 @@ int conv_tc_launch(const TcLayer& t, const ConvProblem* probs, cudaStream_t stre
   prm.out = p.out; prm.out_pitch = p.out_pitch; prm.B = p.B; prm.Ho = p.Ho; prm.Wo = p.Wo; prm.Hfull = p.Hfull; prm.Wfull = p.Wfull;
   prm.osy = p.osy; prm.osx = p.osx; prm.Cout = p.Cout;
   prm.bias = p.bias; prm.leaky = p.leaky;
-  prm.err = tc_error_flag();
-  static bool attr_set = false;
-  if (!attr_set) {
+  TcDeviceState& ds = tc_device_state();
+  if (!ds.err_dev) return fail(DEMON_E_CUDA, "tcgen05 path: no error flag on device %d", ds.device);
+  prm.err = ds.err_dev;
+  if (!ds.tc_attr_set) {
     DEMON_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    attr_set = true;
+    ds.tc_attr_set = true;
   }
   CUtensorMap map;
   memcpy(&map, t.tmap_host, 128);
@@ -462,9 +467,12 @@ int conv_tc_launch(const TcLayer& t, const ConvProblem* probs, cudaStream_t stre
   return DEMON_OK;
 }
 
-int tc_read_error_flag() {
+int tc_read_error_flag(bool clear) {
+  TcDeviceState& ds = tc_device_state();
+  if (!ds.err_dev) return 0;
   int v = 0;
-  cudaMemcpy(&v, tc_error_flag(), sizeof(int), cudaMemcpyDeviceToHost);
+  cudaMemcpy(&v, ds.err_dev, sizeof(int), cudaMemcpyDeviceToHost);
+  if (v && clear) cudaMemset(ds.err_dev, 0, sizeof(int));
   return v;
 }
 

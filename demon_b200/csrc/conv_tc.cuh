@@ -34,10 +34,24 @@ bool tc_halo_supported(const ConvProblem* probs, int nclass);
 int tc_halo_prepare(TcLayer& t, const ConvProblem* probs, const float* const* w_hosts, int nclass, int precision);
 void tc_halo_free(TcLayer& t);
 int conv_tc_halo_launch(const TcLayer& t, const ConvProblem* probs, cudaStream_t stream);
+int tc_halo_describe(const ConvProblem* probs, int nclass, int nsplit, char* buf, int buflen);
 // debug: per-CTA wait-cycle counters of the halo kernel (slots documented in tools/bench_conv.py)
 void tc_halo_enable_timing(bool on);
 int tc_halo_read_timing(long long* host, int nblocks);
-// 1 if any mbarrier wait of the tcgen05 kernel has timed out since process start (pipeline bug detector)
-int tc_read_error_flag();
+// Per-DEVICE launch state of the tensor-core kernels (one process may drive several GPUs): the dynamic shared-memory
+// attribute has to be set on every device a kernel is launched on, the SM count and the pipeline-timeout flag live on
+// the device.  tc_device_state() returns the state of the CURRENT device (cudaGetDevice), creating it on first use.
+struct TcDeviceState {
+  int device = -1;
+  int sms = 148;
+  int* err_dev = nullptr;        // device int: set to 1 by a bounded mbarrier wait that timed out
+  unsigned halo_attr_set = 0;    // bit per conv_tc_halo_kernel instantiation
+  bool tc_attr_set = false;      // conv_tc_kernel
+};
+TcDeviceState& tc_device_state();
+// 1 if an mbarrier wait of a tcgen05 kernel has timed out on the current device since the flag was last cleared
+// (synchronises the device); `clear` resets it.  A timed-out wait lets the kernel run to completion with garbage, so the
+// forward entry points and demon_check_errors() turn this flag into DEMON_E_STATE.
+int tc_read_error_flag(bool clear);
 
 }  // namespace demon

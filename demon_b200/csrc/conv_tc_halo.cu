@@ -1,35 +1,45 @@
 // tcgen05 implicit-GEMM convolution, "halo" variant: every input pixel is fetched ONCE per output tile.
 //
-// conv_tc.cu fetches one shifted 128-pixel A tile per filter tap, i.e. it reads the input kh*kw times (16 times for the
-// four sub-pixel classes of a transposed convolution) and splits it into hi/lo as often; at the resolutions of the
-// first and last layers that makes the kernel L2-bandwidth bound.  Here the output tile is 16 rows x 8 columns and,
-// per 32-channel chunk, ONE TMA box per stride-parity plane brings the tile plus its halo into shared memory
-// ((16+nqy-1) x (8+nqx-1) pixels, 128 bytes per pixel, 128-byte swizzle).  Every tap is then just a different START
-// ADDRESS inside the same shared-memory image:
+// The output tile is 16 rows x 8 columns and, per 32-channel chunk, ONE TMA box per stride-parity plane brings the tile
+// plus its halo into shared memory ((16+nqy-1) x (8+nqx-1) pixels, 128 bytes per pixel, 128-byte swizzle).  Every filter
+// tap is then just a different START ADDRESS inside the same shared-memory image:
 //
 //     GEMM row m = (y, x) of the tile  ->  halo pixel (y + qy - qy_min, x + qx - qx_min)
 //
-// Warp roles (15 warps, persistent over tiles, mbarrier rings between them, every wait bounded):
+// A STEP of the main loop is one (32-channel chunk, input shift) pair.  For a plain convolution a shift is a filter tap;
+// for a transposed convolution k4 s2 (four sub-pixel classes of 2x2 taps each) the 16 class-taps use only NINE distinct
+// input shifts, so the A operand of a shift is staged once and multiplied with the weight blocks of every class that uses
+// it (4 classes at shift (0,0), 2 on the edges, 1 in the corners): 9 steps per chunk instead of 16.
+//
+// Warp roles (persistent over tiles, mbarrier rings between them, every wait bounded):
 //     warp 0        A producer: the halo boxes (TMA)
-//     warp 14       W producer: one pre-swizzled [W_hi ; W_lo] block per (chunk, tap) step (cp.async.bulk); its bytes complete
-//                   on the step's barrier
-//     warps 2..9    stagers, two groups of four alternating steps: shifted pixel rows of the halo image -> registers ->
+//     warp 1        MMA thread: TS-mode tcgen05.mma kind::tf32 (A from TMEM, B = weights from shared memory)
+//     warps 2..     stagers, G groups of four warps taking turns: shifted pixel rows of the halo image -> registers ->
 //                   A_hi (raw fp32) and A_lo = A - trunc_tf32(A) in a TMEM ring slot (tcgen05.st)
-//     warp 1        MMA thread: TS-mode tcgen05.mma kind::tf32 (A from TMEM, B = weights from shared memory), 3xTF32 as two
-//                   stacked instructions for N <= 64, one poll and two commits per step
-//     warps 10..13  epilogue: tcgen05.ld -> transpose through shared memory -> bias, leaky ReLU -> coalesced NHWC stores
+//     next 4 warps  epilogue: tcgen05.ld -> transpose through shared memory -> bias, leaky ReLU -> coalesced NHWC stores
+//     last warp     W producer: the pre-swizzled weight blocks of the step (cp.async.bulk)
 //
-// (The first version of this kernel fed the tap-shifted halo rows to the tensor core directly from shared memory -- a
-// descriptor start shifted by whole 128-byte rows and a stride that is not a multiple of 1024 read exactly the expected
-// rows, because the 128-byte swizzle is applied on ABSOLUTE shared-memory address bits, tools/umma_shift_probe.cu --
-// but a shared-memory A operand costs ~43 cycles per instruction on top of N/2, tools/umma_rate_probe.cu.)
+// ONE operand ring of kRing = 4 slots couples them: slot s = (TMEM columns of A_hi | A_lo, the weight blocks in shared
+// memory, barrier full[s], barrier free[s]).  full[s] collects the four stager warps of the step plus the weight bytes
+// (expect_tx), so the MMA thread polls ONE barrier per step; free[s] is ONE tcgen05.commit per step that releases the TMEM
+// columns to the stagers and the weight slot to the W producer at the same time.
 //
-// All sub-pixel classes of a transposed convolution accumulate side by side in TMEM (nclass x N columns, double
-// buffered when they fit), so the input halo is shared by all 16 taps.  Variants: PER_TAP (images that are not made of
-// whole 16 x 8 tiles: one 128-pixel box per step instead of a halo) and CIN8 (8-channel inputs: four taps per K = 32 step).
+// The MMA thread is the pacemaker of the CTA (profiles/r01_wait_counters.txt: it never waits, it IS the critical path),
+// and what it pays for is its own dependent instruction stream: every value that travels from a vector register to the
+// uniform datapath (R2UR, VOTEU) in front of a UTCHMMA / UTCBAR costs tens of cycles.  The loop is therefore written so
+// that the ring slot is a COMPILE-TIME constant (switch on step & 3 into four copies of the step body): TMEM operand
+// addresses, weight descriptors and barrier addresses are loop-invariant base + immediate, and the only per-step values
+// are the accumulator base (changes per tile) and the class mask of the step.
+//
+// 3xTF32 in two instructions per K8 slice when N <= 64 ("stacked", MODE 1): the weight block holds [W_hi ; W_lo] as 2N
+// consecutive rows, D[:, 0:2N] (+)= A_hi * [W_hi ; W_lo] is ONE UMMA of N' = 2N and D[:, N:2N] += A_lo * W_hi the second;
+// the epilogue adds the halves.  MODE 2 = three instructions (64 < N <= 128, or four classes of N = 64), MODE 0 = plain
+// single-pass TF32.  Variants: PER_TAP (images that are not made of whole 16 x 8 tiles: one 128-pixel TMA box per step
+// instead of a halo) and CIN8 (8-channel inputs: four taps x 8 channels per K = 32 step).
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -40,14 +50,15 @@ namespace demon {
 
 namespace {
 
-constexpr int kStagerWarps = 8;
-constexpr int kWProducerWarp = 2 + kStagerWarps + 4;
-constexpr int kThreads = 32 * (kWProducerWarp + 1);   // 15 warps: A producer, MMA, 8 stagers, 4 epilogue, W producer
+constexpr int kRing = 4;                               // operand ring slots (TMEM A slot of 64 columns + weight slot)
+#ifndef DEMON_MAX_STAGER_GROUPS
+#define DEMON_MAX_STAGER_GROUPS 2
+#endif
+constexpr int kMaxGroups = DEMON_MAX_STAGER_GROUPS;    // stager groups of four warps (3: 19 warps, 96 registers per thread)
+constexpr int kMaxThreads = 32 * (2 + 4 * kMaxGroups + 4 + 1);   // 15 warps with two stager groups
 constexpr int kMaxAStages = 4;
-constexpr int kMaxTStages = 8;
 constexpr int kTileH = 16, kTileW = 8;
 constexpr int kMaxPlanes = 4;
-constexpr int kMaxWStages = 8;
 constexpr int kEpiRowBytes = 144;                  // 32 fp32 + 16 B pad: the epilogue's transpose buffer, conflict free both ways
 constexpr int kEpiStageBytes = 32 * kEpiRowBytes;  // per epilogue warp
 
@@ -60,36 +71,34 @@ struct HaloPlane {
   int bytes;      // rows * cols * 128
 };
 
-struct HaloTap {
-  int plane;
-  int a_off;      // byte offset of the tap's first pixel inside its plane
-  int cls;
-  int first;      // 1: first tap of its class (accumulator starts from zero at chunk 0)
-};
-
 struct HaloParams {
   int tiles_x, tiles_y, B, n_tiles, total_tiles;
   uint32_t mul_n_tiles, mul_tiles_x, mul_tiles_y;   // fast_div multipliers
-  int k_chunks, nplanes, ntaps, nclass;
-  // per-tap mode (layers whose images are not made of whole 16x8 tiles): the A stage is ONE tap's 128-pixel tile
-  // (tb images x th rows x tw columns, one TMA box per (chunk, tap) step, box coordinates carry the tap like in conv_tc.cu)
+  int k_chunks, nplanes, nsteps, nclass;
+  int ngroups;                                      // stager groups (2 or 3)
+  // per step (one input shift of one 32-channel chunk)
+  int st_plane[kMaxTaps], st_aoff[kMaxTaps];        // halo mode: plane and byte offset of the shift's first pixel
+  int st_cmask[kMaxTaps], st_fmask[kMaxTaps];       // classes multiplied in this step / classes that start their sum here (chunk 0)
+  int st_woff[kMaxTaps], st_wbytes[kMaxTaps];       // weight blocks of the step inside a chunk's weight image
+  // per-tap mode (layers whose images are not made of whole 16x8 tiles): the A stage is ONE shift's 128-pixel tile
+  // (tb images x th rows x tw columns, one TMA box per step, box coordinates carry the shift)
   int per_tap, tw, th, tb, tiles_b, aempty_count;
   int tap_c[kMaxTaps], tap_qx[kMaxTaps], tap_ry[kMaxTaps], tap_qy[kMaxTaps];
   // 8-channel mode (Cin == 8, e.g. the image pair): a pixel is 32 bytes in shared memory (no swizzle), the halo is loaded
-  // once per tile, and one K = 32 step gathers FOUR taps x 8 channels into the TMEM A operand (`ntaps` then counts these
+  // once per tile, and one K = 32 step gathers FOUR taps x 8 channels into the TMEM A operand (`nsteps` then counts these
   // groups, g_plane / g_aoff describe the real taps, -1 = missing tap -> zero columns)
   int cin8, ntaps_real;
   int g_plane[kMaxTaps], g_aoff[kMaxTaps];
   HaloPlane planes[kMaxPlanes];
-  HaloTap taps[kMaxTaps];
-  int a_region_bytes;   // hi image of all planes (lo image follows at the same offsets)
+  int a_region_bytes;   // one halo stage (all planes)
   int sa;               // A (halo, shared memory) stages
-  int st;               // A-operand (TMEM) ring slots of 64 columns
-  int w_stage_bytes, sw;
+  int w_chunk_bytes;    // weight bytes of one (n tile, chunk): sum of st_wbytes
+  int w_stage_bytes;    // weight ring slot = the largest step
+  int cls_bytes;        // one class block: [W_hi ; W_lo] (3xTF32) or W alone
   int n_tile, nsplit, tmem_cols;
   int nbuf;             // accumulator buffers (2 = epilogue overlaps the next tile; 1 when TMEM is short)
-  int stacked;          // 1: 3xTF32 as two instructions on [W_hi ; W_lo] (N <= 64), 0: three instructions
-  int acc_w;            // accumulator columns per class: 2 * n_tile in 3xTF32 mode ([big | small] terms), n_tile otherwise
+  int mode;             // 0 single pass, 1 stacked 3xTF32, 2 three-instruction 3xTF32
+  int acc_w;            // accumulator columns per class: 2 * n_tile in stacked mode ([big | small] terms), n_tile otherwise
   const unsigned char* w;
   float* out;
   int out_pitch, Ho, Wo, Hfull, Wfull, osy, osx, Cout;
@@ -113,10 +122,20 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint
   return d;
 }
 
-__device__ __forceinline__ void wait_t(uint32_t bar, uint32_t parity, int* err, long long& acc, bool timed) {
-  if (!timed) { mbar_wait(bar, parity, err); return; }
+// Bounded wait, fully inline (a call in the MMA thread's loop would force every loop-invariant operand of the UTCHMMAs back
+// through a vector register and an R2UR per step).  Fast path: one try_wait.  Slow path: spin with a cycle budget; the
+// cycles spent there go to `acc` (the wait counters of the debug timing cost nothing on the fast path).  On timeout the
+// error flag is raised and the kernel runs to completion with garbage; the host turns the flag into DEMON_E_STATE.
+__device__ __forceinline__ void wait_t(uint32_t bar, uint32_t parity, int* err, long long& acc, bool /*timed*/) {
+  if (mbar_try(bar, parity)) return;
   const long long t0 = clock64();
-  mbar_wait(bar, parity, err);
+  for (;;) {
+    if (mbar_try(bar, parity)) break;
+    if (clock64() - t0 > kTimeoutCycles || *reinterpret_cast<volatile int*>(err) != 0) {
+      atomicExch(err, 1);
+      break;
+    }
+  }
   acc += clock64() - t0;
 }
 
@@ -136,22 +155,90 @@ __device__ __forceinline__ void halo_decode_tile(const HaloParams& p, int tile, 
   else { y0 = yb * kTileH; x0 = xb * kTileW; }
 }
 
-template <bool PER_TAP, bool CIN8>
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
+// ---- MMA thread ---------------------------------------------------------------------------------------------------------
+// loop invariants of the MMA thread (all of them end up as uniform registers or immediates)
+struct MmaCtx {
+  uint32_t full0, free0;      // barrier rings
+  uint32_t t_ring;            // TMEM address of ring slot 0 (A_hi at +0, A_lo at +32)
+  uint32_t w_ring;            // shared-memory address of weight slot 0
+  uint32_t w_stage_bytes, cls_bytes;
+  uint32_t n_tile, acc_w;
+  uint32_t idesc, idesc2;
+  int* err;
+};
+
+// all MMAs of ONE class block of a step: K = 32 as four K8 slices
+template <int MODE>
+__device__ __forceinline__ void issue_block(const MmaCtx& c, uint32_t d, uint32_t a_hi, uint32_t wb, bool fresh) {
+  const uint64_t w_hi = umma_desc_sw128_sbo(wb, 1024);
+  const uint32_t a_lo = a_hi + 32;
+  if (MODE == 1) {
+    // D[:, 0:2N] (+)= A_hi * [W_hi ; W_lo]  (one UMMA of N' = 2N: big term | first small term);  D[:, N:2N] += A_lo * W_hi
+    if (fresh) umma_tf32_ts(d, a_hi, w_hi, c.idesc2, 0u); else umma_tf32_ts(d, a_hi, w_hi, c.idesc2, 1u);
+    umma_tf32_ts(d + c.n_tile, a_lo, w_hi, c.idesc, 1u);
+#pragma unroll
+    for (int j = 1; j < 4; ++j) {   // + 8 TMEM columns / + 32 bytes inside the swizzled weight row per K8 slice
+      umma_tf32_ts(d, a_hi + 8 * j, w_hi + (uint64_t)(2 * j), c.idesc2, 1u);
+      umma_tf32_ts(d + c.n_tile, a_lo + 8 * j, w_hi + (uint64_t)(2 * j), c.idesc, 1u);
+    }
+  } else if (MODE == 2) {
+    const uint64_t w_lo = umma_desc_sw128_sbo(wb + c.n_tile * 128u, 1024);
+    if (fresh) umma_tf32_ts(d, a_hi, w_lo, c.idesc, 0u); else umma_tf32_ts(d, a_hi, w_lo, c.idesc, 1u);
+    umma_tf32_ts(d, a_lo, w_hi, c.idesc, 1u);
+    umma_tf32_ts(d, a_hi, w_hi, c.idesc, 1u);
+#pragma unroll
+    for (int j = 1; j < 4; ++j) {
+      umma_tf32_ts(d, a_hi + 8 * j, w_lo + (uint64_t)(2 * j), c.idesc, 1u);
+      umma_tf32_ts(d, a_lo + 8 * j, w_hi + (uint64_t)(2 * j), c.idesc, 1u);
+      umma_tf32_ts(d, a_hi + 8 * j, w_hi + (uint64_t)(2 * j), c.idesc, 1u);
+    }
+  } else {
+    if (fresh) umma_tf32_ts(d, a_hi, w_hi, c.idesc, 0u); else umma_tf32_ts(d, a_hi, w_hi, c.idesc, 1u);
+#pragma unroll
+    for (int j = 1; j < 4; ++j) umma_tf32_ts(d, a_hi + 8 * j, w_hi + (uint64_t)(2 * j), c.idesc, 1u);
+  }
+}
+
+// one step with the ring slot as a compile-time constant.  `rdy`: the poll of this step's barrier (issued during the
+// previous step) already saw the phase complete; on return it holds the poll of the next step's barrier.
+template <int MODE, int SLOT>
+__device__ __forceinline__ void mma_step(const MmaCtx& c, uint32_t d_base, uint32_t par, uint32_t npar, uint32_t cm, uint32_t fm,
+                                         bool& rdy, long long& w_full, bool timed) {
+  if (!rdy) wait_t(c.full0 + 8 * SLOT, par, c.err, w_full, timed);
+  tc_fence_after();
+  rdy = mbar_try(c.full0 + 8 * ((SLOT + 1) & (kRing - 1)), npar);   // poll the NEXT step's barrier before issuing
+  const uint32_t a_hi = c.t_ring + (uint32_t)(SLOT * 64);
+  uint32_t wb = c.w_ring + (uint32_t)SLOT * c.w_stage_bytes;
+  if (cm == 1u) {
+    issue_block<MODE>(c, d_base, a_hi, wb, (fm & 1u) != 0);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (cm & (1u << k)) {
+        issue_block<MODE>(c, d_base + (uint32_t)k * c.acc_w, a_hi, wb, (fm & (1u << k)) != 0);
+        wb += c.cls_bytes;
+      }
+  }
+  umma_commit(c.free0 + 8 * SLOT);   // ONE commit frees the TMEM columns (stagers) and the weight slot (W producer)
+}
+
+template <bool PER_TAP, bool CIN8, int MODE>
+__global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __grid_constant__ HaloMaps maps, const HaloParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  // bars: A_full[4], A_empty[4], T_full[8], T_empty[8], W_full[8], W_empty[8], accum_full[2], accum_empty[2]
-  __shared__ __align__(8) uint64_t bars[2 * kMaxAStages + 2 * kMaxTStages + 2 * kMaxWStages + 4];
+  // bars: A_full[4], A_empty[4], full[4], free[4], accum_full[2], accum_empty[2]
+  __shared__ __align__(8) uint64_t bars[2 * kMaxAStages + 2 * kRing + 4];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int n_stager_warps = 4 * p.ngroups;
+  const int epi_warp0 = 2 + n_stager_warps;
+  const int w_warp = epi_warp0 + 4;
   const uint32_t afull0 = smem_u32(&bars[0]), aempty0 = smem_u32(&bars[kMaxAStages]);
-  const uint32_t tfull0 = smem_u32(&bars[2 * kMaxAStages]), tempty0 = smem_u32(&bars[2 * kMaxAStages + kMaxTStages]);
-  const uint32_t wfull0 = smem_u32(&bars[2 * kMaxAStages + 2 * kMaxTStages]);
-  const uint32_t wempty0 = smem_u32(&bars[2 * kMaxAStages + 2 * kMaxTStages + kMaxWStages]);
-  const uint32_t cfull0 = smem_u32(&bars[2 * kMaxAStages + 2 * kMaxTStages + 2 * kMaxWStages]);
-  const uint32_t cempty0 = smem_u32(&bars[2 * kMaxAStages + 2 * kMaxTStages + 2 * kMaxWStages + 2]);
+  const uint32_t full0 = smem_u32(&bars[2 * kMaxAStages]), free0 = smem_u32(&bars[2 * kMaxAStages + kRing]);
+  const uint32_t cfull0 = smem_u32(&bars[2 * kMaxAStages + 2 * kRing]);
+  const uint32_t cempty0 = smem_u32(&bars[2 * kMaxAStages + 2 * kRing + 2]);
   const int a_stage_bytes = p.a_region_bytes;
   unsigned char* w_ring = smem + (size_t)p.sa * a_stage_bytes;
 
@@ -161,13 +248,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
       mbar_init(afull0 + 8 * s, 1);
       mbar_init(aempty0 + 8 * s, (uint32_t)p.aempty_count);
     }
-    for (int s = 0; s < kMaxTStages; ++s) {
-      mbar_init(tfull0 + 8 * s, 4 + 1);   // the four warps of the owning stager group + the W producer's expect_tx
-      mbar_init(tempty0 + 8 * s, 1);
-    }
-    for (int s = 0; s < kMaxWStages; ++s) {
-      mbar_init(wfull0 + 8 * s, 1);
-      mbar_init(wempty0 + 8 * s, 1);
+    for (int s = 0; s < kRing; ++s) {
+      mbar_init(full0 + 8 * s, 4 + 1);   // the four warps of the stager group that owns the step + the W producer's expect_tx
+      mbar_init(free0 + 8 * s, 1);       // the MMA thread's commit
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(cfull0 + 8 * s, 1);
@@ -181,9 +264,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   const int acc_cols = p.nclass * p.acc_w;           // columns of one accumulator buffer
-  const uint32_t t_ring = tmem_base + (uint32_t)(p.nbuf * acc_cols);   // A-operand ring: st slots of 64 columns (hi | lo)
+  const uint32_t t_ring = tmem_base + (uint32_t)(p.nbuf * acc_cols);   // A-operand ring: kRing slots of 64 columns (hi | lo)
   const bool timed = p.timing != nullptr;
-  const int steps_per_tile = p.k_chunks * p.ntaps;
+  const int steps_per_tile = p.k_chunks * p.nsteps;
 
   if (warp == 0) {
     // ===== A producer: one halo box per plane and 32-channel chunk ======================================================
@@ -199,7 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
         halo_decode_tile<PER_TAP>(p, tile, nt, n, y0, x0);
         for (int kc = 0; kc < p.k_chunks; ++kc) {
           if (PER_TAP) {
-            for (int t = 0; t < p.ntaps; ++t) {
+            for (int t = 0; t < p.nsteps; ++t) {
               wait_t(aempty0 + 8 * sa, pa ^ 1, p.err, w_aempty, timed);
               mbar_expect_tx(afull0 + 8 * sa, 128u * 128u);
               tma_load_5d(smem_u32(smem + (size_t)sa * a_stage_bytes), &maps.m[0], afull0 + 8 * sa, p.tap_c[t] + kc * 32, x0 + p.tap_qx[t],
@@ -220,121 +303,91 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
       }
       if (timed) { p.timing[blockIdx.x * 16 + 0] = w_aempty; p.timing[blockIdx.x * 16 + 8] = clock64() - t_begin; }
     }
-  } else if (warp == kWProducerWarp) {
-    // ===== W producer: one weight block per (chunk, tap), its own ring ====================================================
-    // The copy's bytes complete on the STEP's barrier (the one the stager group arrives on), so the MMA thread polls one
-    // barrier per step instead of two (a completed poll costs it ~150 cycles, tools/umma_contention_probe.cu).  The weight
-    // ring is at most as deep as the A-operand ring (sw <= st): once W_empty of step s - sw has been committed, step
-    // s - st has long been consumed, i.e. the step barrier is in the phase this expect_tx belongs to.
+  } else if (warp == w_warp) {
+    // ===== W producer: the weight blocks of every step into the step's ring slot ==========================================
+    // The copy's bytes complete on the step's `full` barrier (the one the stager group arrives on).  Both producers of a
+    // slot wait for free[slot] of the previous round before they arrive for the next one, so all five arrivals and the
+    // bytes of a step belong to the same barrier phase.
     if (elect_one_sync()) {
-      int sw = 0, ts = 0;
-      uint32_t pw = 0;
-      long long w_wempty = 0;
+      int slot = 0;
+      uint32_t use = 0;
+      long long w_free = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nt = tile - fast_div(tile, p.n_tiles, p.mul_n_tiles) * p.n_tiles;
-        const unsigned char* wsrc = p.w + (size_t)nt * steps_per_tile * p.w_stage_bytes;
-        for (int kt = 0; kt < steps_per_tile; ++kt) {
-          wait_t(wempty0 + 8 * sw, pw ^ 1, p.err, w_wempty, timed);
-          mbar_expect_tx(tfull0 + 8 * ts, (uint32_t)p.w_stage_bytes);
-          bulk_load(smem_u32(w_ring + (size_t)sw * p.w_stage_bytes), wsrc + (size_t)kt * p.w_stage_bytes, (uint32_t)p.w_stage_bytes,
-                    tfull0 + 8 * ts);
-          if (++sw == p.sw) { sw = 0; pw ^= 1; }
-          if (++ts == p.st) ts = 0;
+        const unsigned char* wsrc = p.w + (size_t)nt * p.k_chunks * p.w_chunk_bytes;
+        for (int kc = 0; kc < p.k_chunks; ++kc, wsrc += p.w_chunk_bytes) {
+          for (int t = 0; t < p.nsteps; ++t) {
+            wait_t(free0 + 8 * slot, use ^ 1, p.err, w_free, timed);
+            const uint32_t bytes = (uint32_t)p.st_wbytes[t];
+            mbar_expect_tx(full0 + 8 * slot, bytes);
+            bulk_load(smem_u32(w_ring + (size_t)slot * p.w_stage_bytes), wsrc + p.st_woff[t], bytes, full0 + 8 * slot);
+            if (++slot == kRing) { slot = 0; use ^= 1; }
+          }
         }
       }
-      if (timed) p.timing[blockIdx.x * 16 + 1] = w_wempty;
+      if (timed) p.timing[blockIdx.x * 16 + 1] = w_free;
     }
   } else if (warp == 1) {
     // ===== MMA issuer: A operand from TMEM (staged by the stager warps), B operand (weights) from shared memory =========
-    // This thread is the pacemaker of the whole CTA, so its per-step overhead is kept minimal: the barrier polls of step
-    // s+1 are issued BEFORE the MMAs of step s and only looked at afterwards (an mbarrier try_wait takes ~90 cycles even
-    // when the phase is already complete), and the per-tap class / first-of-class flags live in two register bitmasks.
     if (elect_one_sync()) {
-      int st = 0, sw = 0;
-      uint32_t pt = 0;
-      // 3xTF32 as TWO instructions per K8 step when N <= 64 ("stacked"): the weight block holds [W_hi ; W_lo] as 2N
-      // consecutive rows, so
-      //   D[:, 0:2N]  (+)= A_hi * [W_hi ; W_lo]      (one UMMA of N' = 2N: big term | first small term)
-      //   D[:, N:2N]   += A_lo * W_hi                 (second small term)
-      // and the epilogue adds the two halves: fewer, wider instructions (the tensor core has a fixed cost per
-      // instruction, tools/umma_rate_probe.cu), and the small terms accumulate apart from the big one.
-      const uint32_t idesc = umma_idesc_tf32(p.n_tile), idesc2 = umma_idesc_tf32(2 * p.n_tile);
-      uint32_t cls_bits = 0, first_bits = 0;
-      for (int t = 0; t < p.ntaps; ++t) { cls_bits |= (uint32_t)p.taps[t].cls << (2 * t); first_bits |= (uint32_t)p.taps[t].first << t; }
-      const uint32_t w_lo_off = (uint32_t)p.n_tile * 128u;
-      const uint32_t w_ring_addr = smem_u32(w_ring);
-      long long w_cempty = 0, w_tfull = 0, w_poll = 0, w_issue = 0, w_commit = 0;
+      MmaCtx c;
+      c.full0 = full0; c.free0 = free0; c.t_ring = t_ring; c.w_ring = smem_u32(w_ring);
+      c.w_stage_bytes = (uint32_t)p.w_stage_bytes; c.cls_bytes = (uint32_t)p.cls_bytes;
+      c.n_tile = (uint32_t)p.n_tile; c.acc_w = (uint32_t)p.acc_w;
+      c.idesc = umma_idesc_tf32(p.n_tile); c.idesc2 = umma_idesc_tf32(2 * p.n_tile);
+      c.err = p.err;
+      // class / fresh masks of the steps of a chunk, four bits per step
+      uint64_t cmasks = 0, fmasks = 0;
+      for (int t = 0; t < p.nsteps; ++t) { cmasks |= (uint64_t)p.st_cmask[t] << (4 * t); fmasks |= (uint64_t)p.st_fmask[t] << (4 * t); }
+      const int nsteps = p.nsteps;
+      long long w_cempty = 0, w_full = 0;
       const long long t_begin = clock64();
       int it = 0;
-      bool rdy_t = mbar_try(tfull0, 0);
+      uint32_t g = 0;   // global step counter of this CTA: slot = g & 3, parity = (g >> 2) & 1
+      bool rdy = mbar_try(full0, 0);
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int a = (p.nbuf == 2) ? (it & 1) : 0;
         const uint32_t cphase = (p.nbuf == 2) ? ((it >> 1) & 1) : (it & 1);
         wait_t(cempty0 + 8 * a, cphase ^ 1, p.err, w_cempty, timed);
         const uint32_t d_base = tmem_base + (uint32_t)(a * acc_cols);
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
-          for (int t = 0; t < p.ntaps; ++t) {
-            const long long tq0 = timed ? clock64() : 0;
-            if (!rdy_t) wait_t(tfull0 + 8 * st, pt, p.err, w_tfull, timed);
-            tc_fence_after();
-            const uint32_t a_hi = t_ring + (uint32_t)(st * 64), a_lo = a_hi + 32;
-            const uint32_t wbase = w_ring_addr + (uint32_t)(sw * p.w_stage_bytes);
-            const int st_cur = st, sw_cur = sw;
-            if (++st == p.st) { st = 0; pt ^= 1; }
-            if (++sw == p.sw) sw = 0;
-            rdy_t = mbar_try(tfull0 + 8 * st, pt);   // poll the NEXT step's barrier
-            const long long tq1 = timed ? clock64() : 0;
-            const uint64_t w_hi = umma_desc_sw128_sbo(wbase, 1024);
-            const uint32_t d_tmem = d_base + ((cls_bits >> (2 * t)) & 3u) * (uint32_t)p.acc_w;
-            const bool fresh = (kc == 0) && ((first_bits >> t) & 1u);
-            if (p.stacked) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {   // 4 x K8: +8 TMEM columns / +32 bytes inside the swizzled weight row
-                umma_tf32_ts(d_tmem, a_hi + 8 * j, w_hi + (uint64_t)(2 * j), idesc2, !(fresh && j == 0));
-                umma_tf32_ts(d_tmem + (uint32_t)p.n_tile, a_lo + 8 * j, w_hi + (uint64_t)(2 * j), idesc, 1);
-              }
-            } else if (p.nsplit == 3) {
-              const uint64_t w_lo = umma_desc_sw128_sbo(wbase + w_lo_off, 1024);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                umma_tf32_ts(d_tmem, a_hi + 8 * j, w_lo + (uint64_t)(2 * j), idesc, !(fresh && j == 0));
-                umma_tf32_ts(d_tmem, a_lo + 8 * j, w_hi + (uint64_t)(2 * j), idesc, 1);
-                umma_tf32_ts(d_tmem, a_hi + 8 * j, w_hi + (uint64_t)(2 * j), idesc, 1);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) umma_tf32_ts(d_tmem, a_hi + 8 * j, w_hi + (uint64_t)(2 * j), idesc, !(fresh && j == 0));
-            }
-            const long long tq2 = timed ? clock64() : 0;
-            umma_commit(tempty0 + 8 * st_cur);
-            umma_commit(wempty0 + 8 * sw_cur);
-            if (kc == p.k_chunks - 1 && t == p.ntaps - 1) umma_commit(cfull0 + 8 * a);
-            if (timed) { const long long tq3 = clock64(); w_poll += tq1 - tq0; w_issue += tq2 - tq1; w_commit += tq3 - tq2; }
+        int t = 0;
+        for (int l = 0; l < steps_per_tile; ++l, ++g) {
+          const uint32_t cm = (uint32_t)(cmasks >> (4 * t)) & 15u;
+          const uint32_t fm = (l < nsteps) ? ((uint32_t)(fmasks >> (4 * t)) & 15u) : 0u;
+          const uint32_t par = (g >> 2) & 1u, npar = ((g + 1) >> 2) & 1u;
+          switch (g & 3u) {
+            case 0: mma_step<MODE, 0>(c, d_base, par, npar, cm, fm, rdy, w_full, timed); break;
+            case 1: mma_step<MODE, 1>(c, d_base, par, npar, cm, fm, rdy, w_full, timed); break;
+            case 2: mma_step<MODE, 2>(c, d_base, par, npar, cm, fm, rdy, w_full, timed); break;
+            default: mma_step<MODE, 3>(c, d_base, par, npar, cm, fm, rdy, w_full, timed); break;
           }
+          if (++t == nsteps) t = 0;
         }
+        umma_commit(cfull0 + 8 * a);   // the tile's accumulators are complete once everything issued so far has retired
       }
       if (timed) {
         long long* tm = p.timing + blockIdx.x * 16;
-        tm[2] = w_cempty; tm[3] = w_tfull; tm[5] = 0; tm[13] = w_poll; tm[14] = w_issue; tm[15] = w_commit; tm[9] = clock64() - t_begin;
+        tm[2] = w_cempty; tm[3] = w_full; tm[9] = clock64() - t_begin;
       }
     }
-  } else if (warp < 2 + kStagerWarps) {
-    // ===== stagers: halo image (shared memory) -> A operand of one tap in TMEM =========================================
-    // Thread (quadrant q, lane l) owns GEMM row m = 32q + l = tile pixel (m / 8, m % 8).  For every (chunk, tap) step it
-    // reads its (shifted) 128-byte pixel out of the swizzled halo image -- conflict free: the 8 lanes of a quarter warp
-    // hit 8 different 16-byte columns -- and writes the raw fp32 values (A_hi: the tensor core ignores the low 13
-    // mantissa bits) and A_lo = A - trunc_tf32(A) to its TMEM lane.  Two groups of four warps alternate steps.
+  } else if (warp < epi_warp0) {
+    // ===== stagers: halo image (shared memory) -> A operand of one shift in TMEM ========================================
+    // Thread (quadrant q, lane l) owns GEMM row m = 32q + l = tile pixel (m / 8, m % 8).  For every step it reads its
+    // (shifted) 128-byte pixel out of the swizzled halo image -- conflict free: the 8 lanes of a quarter warp hit 8
+    // different 16-byte columns -- and writes the raw fp32 values (A_hi: the tensor core ignores the low 13 mantissa bits)
+    // and A_lo = A - trunc_tf32(A) to its TMEM lane.  The groups of four warps take the steps in turns.
     const int q = warp & 3;
     const int grp = (warp - 2) >> 2;
     const int m = q * 32 + lane;
-    const int g = m >> 3, r = m & 7;
+    const int g8 = m >> 3, r = m & 7;
+    const int ngroups = p.ngroups;
     int sa = 0;
     uint32_t pa = 0;
-    long long w_safull = 0, w_tempty = 0;
+    long long w_safull = 0, w_free = 0;
     const long long t_begin = clock64();
-    int step = 0;    // global (chunk, tap) step counter of this CTA
-    int slot = 0;    // = step % st, kept incrementally (no division in the loop)
-    uint32_t use = 0;   // parity of step / st
+    int slot = 0;       // = step % kRing, kept incrementally
+    uint32_t use = 0;   // parity of step / kRing
+    int turn = 0;       // = step % ngroups
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       for (int kc = 0; kc < p.k_chunks; ++kc) {
         uint32_t abase = 0;
@@ -343,23 +396,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
           __syncwarp();
           abase = smem_u32(smem + (size_t)sa * a_stage_bytes);
         }
-        for (int t = 0; t < p.ntaps; ++t, ++step) {
+        for (int t = 0; t < p.nsteps; ++t) {
           const int slot_cur = slot;
           const uint32_t use_cur = use;
-          if (++slot == p.st) { slot = 0; use ^= 1; }
+          if (++slot == kRing) { slot = 0; use ^= 1; }
           const int sa_cur = sa;
           const uint32_t pa_cur = pa;
           if (PER_TAP) { if (++sa == p.sa) { sa = 0; pa ^= 1; } }   // one A stage per step
-          if ((step & 1) != grp) continue;
+          const bool mine = (turn == grp);
+          if (++turn == ngroups) turn = 0;
+          if (!mine) continue;
           uint32_t row;
           if (PER_TAP) {
             wait_t(afull0 + 8 * sa_cur, pa_cur, p.err, w_safull, timed);
             __syncwarp();
-            row = smem_u32(smem + (size_t)sa_cur * a_stage_bytes) + (uint32_t)(g * 1024 + r * 128);
+            row = smem_u32(smem + (size_t)sa_cur * a_stage_bytes) + (uint32_t)(g8 * 1024 + r * 128);
           } else if (!CIN8) {
-            const HaloTap& tp = p.taps[t];
-            const HaloPlane& pl = p.planes[tp.plane];
-            row = abase + (uint32_t)(pl.smem_off + tp.a_off + g * pl.cols * 128 + r * 128);
+            const HaloPlane& pl = p.planes[p.st_plane[t]];
+            row = abase + (uint32_t)(pl.smem_off + p.st_aoff[t] + g8 * pl.cols * 128 + r * 128);
           } else {
             row = 0;
           }
@@ -373,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
               float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
               if (pi >= 0) {
                 const HaloPlane& pl = p.planes[pi];
-                const uint32_t px = abase + (uint32_t)(pl.smem_off + p.g_aoff[rt] + (g * pl.cols + r) * 32);
+                const uint32_t px = abase + (uint32_t)(pl.smem_off + p.g_aoff[rt] + (g8 * pl.cols + r) * 32);
                 v0 = lds128(px); v1 = lds128(px + 16);
               }
               hi[8 * j + 0] = __float_as_uint(v0.x); hi[8 * j + 1] = __float_as_uint(v0.y);
@@ -390,12 +444,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
               hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
             }
           }
-          wait_t(tempty0 + 8 * slot_cur, use_cur ^ 1, p.err, w_tempty, timed);
+          wait_t(free0 + 8 * slot_cur, use_cur ^ 1, p.err, w_free, timed);
           __syncwarp();
           tc_fence_after();
           const uint32_t taddr = t_ring + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot_cur * 64);
           tmem_st_x32(taddr, hi);
-          if (p.nsplit == 3) {
+          if (MODE != 0) {
 #pragma unroll
             for (int c = 0; c < 32; ++c) lo[c] = __float_as_uint(tf32_lo(__uint_as_float(hi[c])));
             tmem_st_x32(taddr + 32, lo);
@@ -404,8 +458,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            mbar_arrive(tfull0 + 8 * slot_cur);
-            if (PER_TAP) mbar_arrive(aempty0 + 8 * sa_cur);   // the tap's tile has been consumed: stage back to the producer
+            mbar_arrive(full0 + 8 * slot_cur);
+            if (PER_TAP) mbar_arrive(aempty0 + 8 * sa_cur);   // the shift's tile has been consumed: stage back to the producer
           }
         }
         if (!PER_TAP) {
@@ -415,21 +469,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
         }
       }
     }
-    if (timed && (threadIdx.x == 64 || threadIdx.x == 64 + 128)) {
-      if (grp == 0) { p.timing[blockIdx.x * 16 + 6] = w_safull; p.timing[blockIdx.x * 16 + 4] = w_tempty; p.timing[blockIdx.x * 16 + 10] = clock64() - t_begin; }
-      else p.timing[blockIdx.x * 16 + 12] = w_tempty;
+    if (timed && lane == 0 && q == 0) {
+      if (grp == 0) { p.timing[blockIdx.x * 16 + 6] = w_safull; p.timing[blockIdx.x * 16 + 4] = w_free; p.timing[blockIdx.x * 16 + 10] = clock64() - t_begin; }
+      else if (grp == 1) p.timing[blockIdx.x * 16 + 12] = w_free;
     }
-  } else if (warp < 2 + kStagerWarps + 4) {
+  } else if (warp < w_warp) {
     // ===== epilogue ======================================================================================================
     // After the TMEM load a thread holds one output pixel (GEMM row) x 32 channels, and consecutive pixels are a whole
-    // pixel pitch apart in global memory: storing rows directly costs 32 memory wavefronts per store instruction, and
-    // the wait counters showed the epilogue (not the MMA thread) bounding the layers with few steps per tile (conv1y,
-    // conv2y: ~3400 / ~9000 cycles per tile).  Each warp therefore transposes its 32 x 32 block through shared memory
-    // (row pitch 144 B: conflict free both ways) and stores with lane = (row % 4, 16-byte chunk), i.e. four pixels x 128
-    // contiguous bytes per instruction; the bias is then one float4 per lane and chunk.
+    // pixel pitch apart in global memory: storing rows directly costs 32 memory wavefronts per store instruction.  Each
+    // warp therefore transposes its 32 x 32 block through shared memory (row pitch 144 B: conflict free both ways) and
+    // stores with lane = (row % 4, 16-byte chunk), i.e. four pixels x 128 contiguous bytes per instruction; the bias is
+    // then one float4 per lane and chunk.
     const int q = warp & 3;
     const int sub = lane >> 3, chunk = lane & 7;
-    const uint32_t stg = smem_u32(w_ring + (size_t)p.sw * p.w_stage_bytes) + (uint32_t)(q * kEpiStageBytes);
+    const uint32_t stg = smem_u32(w_ring + (size_t)kRing * p.w_stage_bytes) + (uint32_t)(q * kEpiStageBytes);
     int rowoff[8];          // element offset of row 4 i + sub of this warp's block inside the output tile
     uint32_t rowpos[8];     // its (yl, xl, nl) for the bounds test
 #pragma unroll
@@ -471,7 +524,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_halo_kernel(const __grid_
           uint32_t v[32];
           const int ncol = (p.n_tile - c0) >= 32 ? 32 : 16;
           if (ncol == 32) tmem_ld_x32(t_row + c0, v); else tmem_ld_x16(t_row + c0, v);
-          if (p.stacked) {   // big term + small terms
+          if (MODE == 1) {   // big term + small terms
             uint32_t u[32];
             if (ncol == 32) tmem_ld_x32(t_row + p.n_tile + c0, u); else tmem_ld_x16(t_row + p.n_tile + c0, u);
             tmem_ld_wait();
@@ -532,143 +585,183 @@ struct HaloPlan {
   HaloParams prm;
   HaloMaps maps;
   int smem_bytes;
+  // weight source of every (step, class): tap index inside the class, -1 = class not in the step
+  int st_tap[kMaxTaps][4];
 };
 
 static int pow2_ceil_h(int v) { int r = 1; while (r < v) r <<= 1; return r; }
+static int popcount4(int m) { return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1) + ((m >> 3) & 1); }
 
-static bool halo_build(const ConvProblem* probs, int nclass, int n_tile_req, int nsplit, HaloPlan& plan, bool encode) {
+static int stager_groups() {
+  static const int g = []() {
+    const char* e = getenv("DEMON_STAGER_GROUPS");
+    int v = e ? atoi(e) : 2;
+    return (v < 1 || v > kMaxGroups) ? 2 : v;
+  }();
+  return g;
+}
+
+// Steps of one chunk: the distinct input shifts of all classes, each with the mask of the classes that use it.
+// max_cls: at most this many classes per step (a wide step needs a wide weight slot; a shift is repeated if necessary).
+struct ShiftStep { int ry, rx, qy, qx, cmask, tap[4]; };
+
+static bool halo_build(const ConvProblem* probs, int nclass, int nsplit, HaloPlan& plan, bool encode) {
   const ConvProblem& p = probs[0];
   HaloParams& prm = plan.prm;
-  memset(&prm, 0, sizeof(prm));
-  prm.nclass = nclass;
-  prm.nsplit = nsplit;
-  prm.cin8 = (p.Cin == 8) ? 1 : 0;
-  const int px_bytes = prm.cin8 ? 32 : 128;   // bytes of one pixel of a halo plane in shared memory
-  prm.per_tap = ((p.Ho % kTileH) != 0 || (p.Wo % kTileW) != 0) ? 1 : 0;
-  if (prm.cin8 && (prm.per_tap || nclass != 1)) return false;
-  int m_tiles = 0;
-  if (prm.per_tap) {
-    // one 128-pixel tile per (chunk, tap) step, tb images x th rows x tw columns (same tiling rule as conv_tc.cu)
-    int ntaps = 0;
+  const int budget = 224 * 1024 - 4 * kEpiStageBytes;   // dynamic shared memory minus the epilogue's transpose buffers
+  // candidates, widest first: classes per step (a wide step needs a wide weight slot), then the N tile cap
+  struct Cand { int max_cls, n_cap; };
+  std::vector<Cand> cands;
+  for (int mc = nclass; mc >= 1; mc = (mc > 2 ? 2 : mc - 1)) cands.push_back({mc, 256});
+  cands.push_back({1, 64});
+  cands.push_back({1, 32});
+  bool found = false;
+  for (const Cand& cand : cands) {
+    const int max_cls = cand.max_cls;
+    memset(&prm, 0, sizeof(prm));
+    memset(plan.st_tap, -1, sizeof(plan.st_tap));
+    prm.nclass = nclass;
+    prm.nsplit = nsplit;
+    prm.ngroups = stager_groups();
+    prm.cin8 = (p.Cin == 8) ? 1 : 0;
+    const int px_bytes = prm.cin8 ? 32 : 128;   // bytes of one pixel of a halo plane in shared memory
+    prm.per_tap = ((p.Ho % kTileH) != 0 || (p.Wo % kTileW) != 0) ? 1 : 0;
+    if (prm.cin8 && (prm.per_tap || nclass != 1)) return false;
+    // ---- steps ---------------------------------------------------------------------------------------------------
+    std::vector<ShiftStep> steps;
     for (int c = 0; c < nclass; ++c)
-      for (int i = 0; i < probs[c].ntaps; ++i, ++ntaps) {
-        if (ntaps >= kMaxTaps) return false;
-        const int qy = floor_div_h(probs[c].dy[i], p.sy), qx = floor_div_h(probs[c].dx[i], p.sx);
-        prm.tap_qy[ntaps] = qy; prm.tap_ry[ntaps] = probs[c].dy[i] - qy * p.sy;
-        prm.tap_qx[ntaps] = qx; prm.tap_c[ntaps] = (probs[c].dx[i] - qx * p.sx) * p.in_pitch;
-        prm.taps[ntaps].plane = 0; prm.taps[ntaps].a_off = 0; prm.taps[ntaps].cls = c; prm.taps[ntaps].first = (i == 0) ? 1 : 0;
+      for (int i = 0; i < probs[c].ntaps; ++i) {
+        const int qy = floor_div_h(probs[c].dy[i], p.sy), ry = probs[c].dy[i] - qy * p.sy;
+        const int qx = floor_div_h(probs[c].dx[i], p.sx), rx = probs[c].dx[i] - qx * p.sx;
+        int si = -1;
+        for (size_t k = 0; k < steps.size(); ++k)
+          if (steps[k].ry == ry && steps[k].rx == rx && steps[k].qy == qy && steps[k].qx == qx && !((steps[k].cmask >> c) & 1) &&
+              popcount4(steps[k].cmask) < max_cls) { si = (int)k; break; }
+        if (si < 0) { steps.push_back({ry, rx, qy, qx, 0, {-1, -1, -1, -1}}); si = (int)steps.size() - 1; }
+        steps[si].cmask |= 1 << c;
+        steps[si].tap[c] = i;
       }
-    prm.ntaps = ntaps;
-    prm.nplanes = 1;
-    long best_tiles = -1;
-    const int tw = std::min(128, pow2_ceil_h(p.Wo));
-    for (int th = 1; th * tw <= 128; th <<= 1) {
-      const int tb = 128 / (tw * th);
-      const long tiles = (long)ceil_div(p.Wo, tw) * ceil_div(p.Ho, th) * ceil_div(p.B, tb);
-      if (best_tiles < 0 || tiles <= best_tiles) {
-        best_tiles = tiles;
-        prm.tw = tw; prm.th = th; prm.tb = tb;
-        prm.tiles_x = ceil_div(p.Wo, tw); prm.tiles_y = ceil_div(p.Ho, th); prm.tiles_b = ceil_div(p.B, tb);
+    const int nreal = (int)steps.size();
+    if (nreal > kMaxTaps) return false;
+    int m_tiles = 0;
+    if (prm.per_tap) {
+      // one 128-pixel tile per step, tb images x th rows x tw columns
+      for (int t = 0; t < nreal; ++t) {
+        prm.tap_qy[t] = steps[t].qy; prm.tap_ry[t] = steps[t].ry;
+        prm.tap_qx[t] = steps[t].qx; prm.tap_c[t] = steps[t].rx * p.in_pitch;
       }
+      prm.nplanes = 1;
+      long best_tiles = -1;
+      const int tw = std::min(128, pow2_ceil_h(p.Wo));
+      for (int th = 1; th * tw <= 128; th <<= 1) {
+        const int tb = 128 / (tw * th);
+        const long tiles = (long)ceil_div(p.Wo, tw) * ceil_div(p.Ho, th) * ceil_div(p.B, tb);
+        if (best_tiles < 0 || tiles <= best_tiles) {
+          best_tiles = tiles;
+          prm.tw = tw; prm.th = th; prm.tb = tb;
+          prm.tiles_x = ceil_div(p.Wo, tw); prm.tiles_y = ceil_div(p.Ho, th); prm.tiles_b = ceil_div(p.B, tb);
+        }
+      }
+      prm.planes[0].cols = prm.tw; prm.planes[0].rows = prm.th; prm.planes[0].bytes = 128 * 128;
+      prm.a_region_bytes = 128 * 128;
+      prm.aempty_count = 4;     // the four stager warps of the group that consumed the shift release its shared-memory stage
+      m_tiles = prm.tiles_x * prm.tiles_y * prm.tiles_b;
+    } else {
+      prm.aempty_count = 4 * prm.ngroups;
+      // planes: shifts grouped by stride parity
+      struct PInfo { int ry, rx, qy_min, qy_max, qx_min, qx_max; };
+      std::vector<PInfo> pinfo;
+      std::vector<int> step_plane(nreal);
+      for (int t = 0; t < nreal; ++t) {
+        int pi = -1;
+        for (size_t k = 0; k < pinfo.size(); ++k)
+          if (pinfo[k].ry == steps[t].ry && pinfo[k].rx == steps[t].rx) pi = (int)k;
+        if (pi < 0) { pinfo.push_back({steps[t].ry, steps[t].rx, steps[t].qy, steps[t].qy, steps[t].qx, steps[t].qx}); pi = (int)pinfo.size() - 1; }
+        PInfo& pl = pinfo[pi];
+        pl.qy_min = std::min(pl.qy_min, steps[t].qy); pl.qy_max = std::max(pl.qy_max, steps[t].qy);
+        pl.qx_min = std::min(pl.qx_min, steps[t].qx); pl.qx_max = std::max(pl.qx_max, steps[t].qx);
+        step_plane[t] = pi;
+      }
+      if ((int)pinfo.size() > kMaxPlanes) return false;
+      prm.nplanes = (int)pinfo.size();
+      int off = 0;
+      for (int i = 0; i < prm.nplanes; ++i) {
+        HaloPlane& pl = prm.planes[i];
+        pl.c_off = pinfo[i].rx * p.in_pitch; pl.ry = pinfo[i].ry;
+        pl.qx_min = pinfo[i].qx_min; pl.qy_min = pinfo[i].qy_min;
+        pl.cols = kTileW + pinfo[i].qx_max - pinfo[i].qx_min;
+        pl.rows = kTileH + pinfo[i].qy_max - pinfo[i].qy_min;
+        if (pl.cols > 256 || pl.rows > 256) return false;
+        pl.bytes = pl.rows * pl.cols * px_bytes;
+        pl.smem_off = off;
+        off += (pl.bytes + 1023) / 1024 * 1024;
+      }
+      prm.a_region_bytes = off;
+      for (int t = 0; t < nreal; ++t) {
+        const HaloPlane& pl = prm.planes[step_plane[t]];
+        prm.st_plane[t] = step_plane[t];
+        prm.st_aoff[t] = ((steps[t].qy - pl.qy_min) * pl.cols + (steps[t].qx - pl.qx_min)) * px_bytes;
+      }
+      prm.tiles_x = ceil_div(p.Wo, kTileW); prm.tiles_y = ceil_div(p.Ho, kTileH); prm.tiles_b = p.B;
+      m_tiles = prm.tiles_x * prm.tiles_y * p.B;
     }
-    prm.planes[0].cols = prm.tw; prm.planes[0].rows = prm.th; prm.planes[0].bytes = 128 * 128;
-    prm.a_region_bytes = 128 * 128;
-    prm.aempty_count = 4;     // the four stager warps of the group that consumed the tap release its shared-memory stage
-    m_tiles = prm.tiles_x * prm.tiles_y * prm.tiles_b;
-  } else {
-  prm.aempty_count = kStagerWarps;
-  // planes: taps grouped by stride parity
-  struct PInfo { int ry, rx, qy_min, qy_max, qx_min, qx_max; };
-  std::vector<PInfo> pinfo;
-  struct TInfo { int plane, qy, qx, cls; };
-  std::vector<TInfo> tinfo;
-  for (int c = 0; c < nclass; ++c)
-    for (int i = 0; i < probs[c].ntaps; ++i) {
-      const int qy = floor_div_h(probs[c].dy[i], p.sy), ry = probs[c].dy[i] - qy * p.sy;
-      const int qx = floor_div_h(probs[c].dx[i], p.sx), rx = probs[c].dx[i] - qx * p.sx;
-      int pi = -1;
-      for (size_t k = 0; k < pinfo.size(); ++k)
-        if (pinfo[k].ry == ry && pinfo[k].rx == rx) pi = (int)k;
-      if (pi < 0) { pinfo.push_back({ry, rx, qy, qy, qx, qx}); pi = (int)pinfo.size() - 1; }
-      PInfo& pl = pinfo[pi];
-      pl.qy_min = std::min(pl.qy_min, qy); pl.qy_max = std::max(pl.qy_max, qy);
-      pl.qx_min = std::min(pl.qx_min, qx); pl.qx_max = std::max(pl.qx_max, qx);
-      tinfo.push_back({pi, qy, qx, c});
+    // class / fresh masks, weight source of every (step, class)
+    int seen = 0;
+    for (int t = 0; t < nreal; ++t) {
+      prm.st_cmask[t] = steps[t].cmask;
+      prm.st_fmask[t] = steps[t].cmask & ~seen;
+      seen |= steps[t].cmask;
+      for (int c = 0; c < 4; ++c) plan.st_tap[t][c] = steps[t].tap[c];
     }
-  if ((int)pinfo.size() > kMaxPlanes || (int)tinfo.size() > kMaxTaps) return false;
-  prm.nplanes = (int)pinfo.size();
-  prm.ntaps = (int)tinfo.size();
-  int off = 0;
-  for (int i = 0; i < prm.nplanes; ++i) {
-    HaloPlane& pl = prm.planes[i];
-    pl.c_off = pinfo[i].rx * p.in_pitch; pl.ry = pinfo[i].ry;
-    pl.qx_min = pinfo[i].qx_min; pl.qy_min = pinfo[i].qy_min;
-    pl.cols = kTileW + pinfo[i].qx_max - pinfo[i].qx_min;
-    pl.rows = kTileH + pinfo[i].qy_max - pinfo[i].qy_min;
-    if (pl.cols > 256 || pl.rows > 256) return false;
-    pl.bytes = pl.rows * pl.cols * px_bytes;
-    pl.smem_off = off;
-    off += (pl.bytes + 1023) / 1024 * 1024;
+    prm.nsteps = nreal;
+    if (prm.cin8) {   // regroup: one K step = four consecutive taps (nclass == 1: every real step is one tap of class 0)
+      prm.ntaps_real = nreal;
+      for (int t = 0; t < nreal; ++t) { prm.g_plane[t] = prm.st_plane[t]; prm.g_aoff[t] = prm.st_aoff[t]; }
+      prm.nsteps = (nreal + 3) / 4;
+      for (int t = 0; t < prm.nsteps; ++t) { prm.st_plane[t] = 0; prm.st_aoff[t] = 0; prm.st_cmask[t] = 1; prm.st_fmask[t] = (t == 0) ? 1 : 0; }
+    }
+    // ---- TMEM budget (512 columns): nbuf accumulator buffers x nclass x acc_w  +  the A-operand ring, kRing slots of 64
+    // columns (A_hi | A_lo of one shift).  acc_w = 2N in stacked 3xTF32 mode (big | small terms side by side), N otherwise.
+    const int ring_cols = kRing * 64;
+    const int cout16 = (p.Cout + 15) / 16 * 16;
+    int n_tile = std::min(std::min(cout16, nsplit == 1 ? 256 : 128), cand.n_cap);
+    while (n_tile > 16 && nclass * n_tile + ring_cols > 512) n_tile = (n_tile > 32) ? (n_tile / 2 + 15) / 16 * 16 : n_tile - 16;
+    // narrow the N tile (down to 64) while the layer would leave SMs idle
+    while (n_tile >= 128 && (n_tile % 32) == 0 && (long)m_tiles * ceil_div(p.Cout, n_tile) < 148) n_tile /= 2;
+    if (n_tile < 16 || nclass * n_tile + ring_cols > 512) return false;
+    prm.mode = (nsplit == 1) ? 0 : 2;
+    if (nsplit == 3 && n_tile <= 64 && nclass * 2 * n_tile + ring_cols <= 512) prm.mode = 1;
+    prm.n_tile = n_tile;
+    prm.acc_w = (prm.mode == 1 ? 2 : 1) * n_tile;
+    prm.nbuf = (2 * nclass * prm.acc_w + ring_cols <= 512) ? 2 : 1;
+    prm.n_tiles = ceil_div(p.Cout, n_tile);
+    int cols = 32;
+    while (cols < prm.nbuf * nclass * prm.acc_w + ring_cols) cols <<= 1;
+    prm.tmem_cols = cols;
+    prm.k_chunks = prm.cin8 ? 1 : p.Cin / 32;
+    // ---- weights: one class block = [W_hi ; W_lo] (3xTF32) or W alone, 1024-byte aligned; a step holds the blocks of its
+    // classes in ascending class order; the ring slot is as large as the widest step
+    prm.cls_bytes = (nsplit == 3) ? n_tile * 256 : (n_tile * 128 + 1023) / 1024 * 1024;
+    int woff = 0, wmax = 0;
+    for (int t = 0; t < prm.nsteps; ++t) {
+      prm.st_woff[t] = woff;
+      prm.st_wbytes[t] = popcount4(prm.st_cmask[t]) * prm.cls_bytes;
+      woff += prm.st_wbytes[t];
+      wmax = std::max(wmax, prm.st_wbytes[t]);
+    }
+    prm.w_chunk_bytes = woff;
+    prm.w_stage_bytes = wmax;
+    // shared memory: the weight ring, then up to 4 halo stages (at least 2)
+    const int rest = budget - kRing * wmax;
+    if (rest < 2 * prm.a_region_bytes) continue;   // next candidate: narrower steps / narrower N tile
+    prm.sa = std::min(kMaxAStages, rest / prm.a_region_bytes);
+    plan.smem_bytes = prm.sa * prm.a_region_bytes + kRing * wmax + 4 * kEpiStageBytes + 1024;
+    found = true;
+    break;
   }
-  prm.a_region_bytes = off;
-  int last_cls = -1;
-  for (int t = 0; t < prm.ntaps; ++t) {
-    HaloTap& tp = prm.taps[t];
-    const HaloPlane& pl = prm.planes[tinfo[t].plane];
-    tp.plane = tinfo[t].plane;
-    tp.a_off = ((tinfo[t].qy - pl.qy_min) * pl.cols + (tinfo[t].qx - pl.qx_min)) * px_bytes;
-    tp.cls = tinfo[t].cls;
-    tp.first = (tp.cls != last_cls) ? 1 : 0;
-    last_cls = tp.cls;
-  }
-  if (prm.cin8) {   // regroup: one K step = four consecutive taps
-    prm.ntaps_real = prm.ntaps;
-    for (int t = 0; t < prm.ntaps_real; ++t) { prm.g_plane[t] = prm.taps[t].plane; prm.g_aoff[t] = prm.taps[t].a_off; }
-    prm.ntaps = (prm.ntaps_real + 3) / 4;
-    for (int t = 0; t < prm.ntaps; ++t) { prm.taps[t].plane = 0; prm.taps[t].a_off = 0; prm.taps[t].cls = 0; prm.taps[t].first = (t == 0) ? 1 : 0; }
-  }
-  prm.tiles_x = ceil_div(p.Wo, kTileW); prm.tiles_y = ceil_div(p.Ho, kTileH); prm.tiles_b = p.B;
-  m_tiles = prm.tiles_x * prm.tiles_y * p.B;
-  }
-  // TMEM budget (512 columns): nbuf accumulator buffers x nclass x acc_w  +  the A-operand ring, `st` slots of 64
-  // columns (A_hi | A_lo of one tap), at least 4 slots so that the stagers run ahead of the tensor core.
-  // acc_w = 2N in stacked 3xTF32 mode (big | small terms side by side, see the MMA role), N otherwise.
-  const int cout16 = (p.Cout + 15) / 16 * 16;
-  auto fits = [&](int n, int wm, int& nbuf_out) {
-    for (int nb = 2; nb >= 1; --nb)
-      if (nb * nclass * wm * n + 4 * 64 <= 512) { nbuf_out = nb; return true; }
-    return false;
-  };
-  int n_tile = std::min(cout16, 256), nbuf = 2;
-  while (n_tile >= 16 && !fits(n_tile, 1, nbuf)) n_tile = (n_tile > 32) ? (n_tile / 2 + 15) / 16 * 16 : n_tile - 16;
-  if (n_tile_req > 0) n_tile = std::min(n_tile, n_tile_req);
-  // narrow the N tile (down to 64) while the layer would leave SMs idle
-  while (n_tile >= 128 && (n_tile % 32) == 0 && (long)m_tiles * ceil_div(p.Cout, n_tile) < 148) n_tile /= 2;
-  if (n_tile < 16 || !fits(n_tile, 1, nbuf)) return false;
-  prm.stacked = 0;
-  int nbuf2 = 0;
-  if (nsplit == 3 && n_tile <= 64 && fits(n_tile, 2, nbuf2)) { prm.stacked = 1; nbuf = nbuf2; }
-  prm.nbuf = nbuf;
-  prm.n_tile = n_tile;
-  prm.acc_w = (prm.stacked ? 2 : 1) * n_tile;
-  prm.n_tiles = ceil_div(p.Cout, n_tile);
-  prm.st = std::min(kMaxTStages, (512 - prm.nbuf * nclass * prm.acc_w) / 64);
-  int cols = 32;
-  while (cols < prm.nbuf * nclass * prm.acc_w + prm.st * 64) cols <<= 1;
-  prm.tmem_cols = cols;
-  prm.k_chunks = prm.cin8 ? 1 : p.Cin / 32;
-  // weight ring slot = one (chunk, tap) block: [W_hi | W_lo] (3xTF32) or W_hi alone, 1024-byte aligned
-  const int slot = (nsplit == 3) ? n_tile * 256 : (n_tile * 128 + 1023) / 1024 * 1024;
-  prm.w_stage_bytes = slot;
-  // shared memory: up to 4 halo stages (at least 2), the rest for the weight ring
-  const int budget = 224 * 1024 - 4 * kEpiStageBytes;   // minus the epilogue's transpose buffers
-  prm.sa = kMaxAStages;
-  while (prm.sa > 2 && budget - prm.sa * prm.a_region_bytes < 4 * slot) --prm.sa;
-  const int rest = budget - prm.sa * prm.a_region_bytes;
-  if (rest < 2 * slot) return false;
-  prm.sw = std::min(std::min(kMaxWStages, prm.st), rest / slot);   // sw <= st, see the W producer
-  plan.smem_bytes = prm.sa * prm.a_region_bytes + prm.sw * slot + 4 * kEpiStageBytes + 1024;
+  if (!found || prm.sa < 2) return false;
   prm.B = p.B;
+  const int m_tiles = prm.tiles_x * prm.tiles_y * prm.tiles_b;
   prm.total_tiles = m_tiles * prm.n_tiles;
   auto fd = [](int d) { return d <= 1 ? 0u : (uint32_t)((1ull << 32) / (uint64_t)d + 1ull); };
   prm.mul_n_tiles = fd(prm.n_tiles); prm.mul_tiles_x = fd(prm.tiles_x); prm.mul_tiles_y = fd(prm.tiles_y);
@@ -677,7 +770,7 @@ static bool halo_build(const ConvProblem* probs, int nclass, int n_tile_req, int
   prm.osy = p.osy; prm.osx = p.osx; prm.Cout = p.Cout; prm.bias = p.bias; prm.leaky = p.leaky;
   for (int c = 0; c < nclass; ++c) { prm.cls_ooy[c] = probs[c].ooy; prm.cls_oox[c] = probs[c].oox; }
   if (!encode) return true;
-  // TMA descriptors: same 5-D view as conv_tc.cu, one box shape per plane
+  // TMA descriptors: 5-D view {sx*C, W/sx, sy, H/sy, B} of the input slice, one box shape per plane
   typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -705,17 +798,28 @@ static bool halo_build(const ConvProblem* probs, int nclass, int n_tile_req, int
 }
 
 bool tc_halo_supported(const ConvProblem* probs, int nclass) {
-  const ConvProblem& p = probs[0];
+  if (nclass < 1 || nclass > 4) return false;
   for (int c = 0; c < nclass; ++c) {
     ConvProblem q = probs[c];
     if (q.Cin == 8 && q.in_pitch == 8) q.Cin = 32;   // 8-channel mode: everything but the channel rule must hold
     if (!tc_layer_supported(q)) return false;
+    if (probs[c].in != probs[0].in || probs[c].Cout != probs[0].Cout || probs[c].sy != probs[0].sy || probs[c].sx != probs[0].sx) return false;
   }
-  // per-tap TS mode pays off for plain convolutions at low resolution; the 4-class transposed convolutions there are
-  // TMEM-limited (single accumulator buffer, split N) and stay on the shared-memory-operand kernel (conv_tc.cu)
-  if (((p.Ho % kTileH) != 0 || (p.Wo % kTileW) != 0) && nclass != 1) return false;
   HaloPlan plan;
-  return halo_build(probs, nclass, 0, 3, plan, false);
+  return halo_build(probs, nclass, 3, plan, false);
+}
+
+// debug: the plan halo_build chooses for a layer, as text (no device needed)
+int tc_halo_describe(const ConvProblem* probs, int nclass, int nsplit, char* buf, int buflen) {
+  HaloPlan plan;
+  if (!halo_build(probs, nclass, nsplit, plan, false)) return snprintf(buf, buflen, "halo: unsupported");
+  const HaloParams& q = plan.prm;
+  int n = snprintf(buf, buflen, "halo %s mode %d n_tile %d x%d nbuf %d tmem %d steps %d x %d chunks sa %d a_stage %d w_slot %d smem %d tiles %d groups %d |",
+                   q.per_tap ? "per-tap" : (q.cin8 ? "cin8" : "halo"), q.mode, q.n_tile, q.n_tiles, q.nbuf, q.tmem_cols, q.nsteps, q.k_chunks, q.sa,
+                   q.a_region_bytes, q.w_stage_bytes, plan.smem_bytes, q.total_tiles, q.ngroups);
+  for (int t = 0; t < q.nsteps && n < buflen - 32; ++t)
+    n += snprintf(buf + n, buflen - n, " [c%x f%x w%d+%d]", q.st_cmask[t], q.st_fmask[t], q.st_woff[t], q.st_wbytes[t]);
+  return n;
 }
 
 static float tf32_round_h(float x) {
@@ -733,39 +837,39 @@ int tc_halo_prepare(TcLayer& t, const ConvProblem* probs, const float* const* w_
   const ConvProblem& p = probs[0];
   const int nsplit = (precision == DEMON_PREC_TF32) ? 1 : 3;
   HaloPlan* plan = new HaloPlan();
-  if (!halo_build(probs, nclass, 0, nsplit, *plan, true)) {
+  if (!halo_build(probs, nclass, nsplit, *plan, true)) {
     delete plan;
     return fail(DEMON_E_CUDA, "tc_halo_prepare: could not build the plan (tensor map encode failed?)");
   }
   const HaloParams& prm = plan->prm;
-  // weights: [n_tile][chunk][tap (class major)] blocks of [W_hi | W_lo], n_tile rows x 32 fp32, K-major, pre-swizzled
-  const int slot = prm.w_stage_bytes;
-  const size_t total = (size_t)prm.n_tiles * prm.k_chunks * prm.ntaps * slot;
+  // weights: [n tile][chunk][step][class of the step] blocks of [W_hi | W_lo], n_tile rows x 32 fp32, K-major, pre-swizzled
+  const size_t total = (size_t)prm.n_tiles * prm.k_chunks * prm.w_chunk_bytes;
   std::vector<unsigned char> packed(total, 0);
-  std::vector<int> tap_in_class(prm.ntaps);
-  {
-    int cnt[4] = {0, 0, 0, 0};
-    for (int tt = 0; tt < prm.ntaps; ++tt) tap_in_class[tt] = cnt[prm.taps[tt].cls]++;
-  }
   for (int nt = 0; nt < prm.n_tiles; ++nt)
     for (int kc = 0; kc < prm.k_chunks; ++kc)
-      for (int tt = 0; tt < prm.ntaps; ++tt) {
-        unsigned char* blk = packed.data() + ((size_t)(nt * prm.k_chunks + kc) * prm.ntaps + tt) * slot;
-        const int cls = prm.taps[tt].cls, tap = tap_in_class[tt];
-        for (int r = 0; r < prm.n_tile; ++r) {
-          const int co = nt * prm.n_tile + r;
-          for (int k = 0; k < 32; ++k) {
-            float w = 0.f;
-            if (prm.cin8) {   // K index = (tap within the group of four, channel)
-              const int rt = 4 * tt + k / 8;
-              if (co < p.Cout && rt < prm.ntaps_real) w = w_hosts[0][((size_t)rt * 8 + (k & 7)) * p.Cout_pad + co];
-            } else
-            if (co < p.Cout) w = w_hosts[cls][((size_t)tap * p.Cin + kc * 32 + k) * p.Cout_pad + co];
-            const float hi = (nsplit == 3) ? tf32_round_h(w) : w;
-            const float lo = w - hi;
-            const size_t off = (size_t)r * 128 + (size_t)(((k >> 2) ^ (r & 7)) << 4) + (size_t)(k & 3) * 4;
-            memcpy(blk + off, &hi, 4);
-            if (nsplit == 3) memcpy(blk + (size_t)prm.n_tile * 128 + off, &lo, 4);
+      for (int tt = 0; tt < prm.nsteps; ++tt) {
+        int idx = 0;
+        for (int cls = 0; cls < 4; ++cls) {
+          if (!((prm.st_cmask[tt] >> cls) & 1)) continue;
+          unsigned char* blk = packed.data() + ((size_t)nt * prm.k_chunks + kc) * prm.w_chunk_bytes + prm.st_woff[tt] + (size_t)idx * prm.cls_bytes;
+          ++idx;
+          const int tap = prm.cin8 ? 0 : plan->st_tap[tt][cls];
+          for (int r = 0; r < prm.n_tile; ++r) {
+            const int co = nt * prm.n_tile + r;
+            for (int k = 0; k < 32; ++k) {
+              float w = 0.f;
+              if (prm.cin8) {   // K index = (tap within the group of four, channel)
+                const int rt = 4 * tt + k / 8;
+                if (co < p.Cout && rt < prm.ntaps_real) w = w_hosts[0][((size_t)plan->st_tap[rt][0] * 8 + (k & 7)) * p.Cout_pad + co];
+              } else if (co < p.Cout) {
+                w = w_hosts[cls][((size_t)tap * p.Cin + kc * 32 + k) * p.Cout_pad + co];
+              }
+              const float hi = (nsplit == 3) ? tf32_round_h(w) : w;
+              const float lo = w - hi;
+              const size_t off = (size_t)r * 128 + (size_t)(((k >> 2) ^ (r & 7)) << 4) + (size_t)(k & 3) * 4;
+              memcpy(blk + off, &hi, 4);
+              if (nsplit == 3) memcpy(blk + (size_t)prm.n_tile * 128 + off, &lo, 4);
+            }
           }
         }
       }
@@ -788,8 +892,6 @@ void tc_halo_free(TcLayer& t) {
   t.halo_plan = nullptr;
 }
 
-extern int* tc_error_flag();
-
 static long long* g_timing_dev = nullptr;
 void tc_halo_enable_timing(bool on) {
   if (on && !g_timing_dev) { cudaMalloc(&g_timing_dev, 256 * 16 * sizeof(long long)); }
@@ -802,30 +904,43 @@ int tc_halo_read_timing(long long* host, int nblocks) {
   return 0;
 }
 
+template <bool PER_TAP, bool CIN8, int MODE>
+static int launch_variant(const HaloPlan* plan, const HaloParams& prm, int grid, int threads, cudaStream_t stream) {
+  TcDeviceState& ds = tc_device_state();
+  const int slot = (PER_TAP ? 1 : 0) + (CIN8 ? 2 : 0) + 3 * MODE;
+  if (!(ds.halo_attr_set & (1u << slot))) {
+    DEMON_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<PER_TAP, CIN8, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    ds.halo_attr_set |= 1u << slot;
+  }
+  conv_tc_halo_kernel<PER_TAP, CIN8, MODE><<<grid, threads, plan->smem_bytes, stream>>>(plan->maps, prm);
+  DEMON_LAUNCH_CHECK();
+  return DEMON_OK;
+}
+
 int conv_tc_halo_launch(const TcLayer& t, const ConvProblem* probs, cudaStream_t stream) {
   HaloPlan* plan = static_cast<HaloPlan*>(t.halo_plan);
   HaloParams prm = plan->prm;
   prm.out = probs[0].out;          // the output slice may be re-pointed between calls (caller-owned result buffers)
   prm.out_pitch = probs[0].out_pitch;
-  prm.err = tc_error_flag();
+  TcDeviceState& ds = tc_device_state();
+  if (!ds.err_dev) return fail(DEMON_E_CUDA, "tcgen05 path: no error flag on device %d", ds.device);
+  prm.err = ds.err_dev;
   prm.timing = g_timing_dev;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DEMON_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    DEMON_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    DEMON_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    attr_set = true;
+  const int grid = std::min(prm.total_tiles, ds.sms);
+  const int threads = 32 * (2 + 4 * prm.ngroups + 4 + 1);
+  if (prm.per_tap) {
+    if (prm.mode == 0) return launch_variant<true, false, 0>(plan, prm, grid, threads, stream);
+    if (prm.mode == 1) return launch_variant<true, false, 1>(plan, prm, grid, threads, stream);
+    return launch_variant<true, false, 2>(plan, prm, grid, threads, stream);
   }
-  int sms = 0, dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (sms <= 0) sms = 148;
-  const int grid = std::min(prm.total_tiles, sms);
-  if (prm.per_tap) conv_tc_halo_kernel<true, false><<<grid, kThreads, plan->smem_bytes, stream>>>(plan->maps, prm);
-  else if (prm.cin8) conv_tc_halo_kernel<false, true><<<grid, kThreads, plan->smem_bytes, stream>>>(plan->maps, prm);
-  else conv_tc_halo_kernel<false, false><<<grid, kThreads, plan->smem_bytes, stream>>>(plan->maps, prm);
-  DEMON_LAUNCH_CHECK();
-  return DEMON_OK;
+  if (prm.cin8) {
+    if (prm.mode == 0) return launch_variant<false, true, 0>(plan, prm, grid, threads, stream);
+    if (prm.mode == 1) return launch_variant<false, true, 1>(plan, prm, grid, threads, stream);
+    return launch_variant<false, true, 2>(plan, prm, grid, threads, stream);
+  }
+  if (prm.mode == 0) return launch_variant<false, false, 0>(plan, prm, grid, threads, stream);
+  if (prm.mode == 1) return launch_variant<false, false, 1>(plan, prm, grid, threads, stream);
+  return launch_variant<false, false, 2>(plan, prm, grid, threads, stream);
 }
 
 }  // namespace demon

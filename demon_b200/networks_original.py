@@ -20,6 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from ._lib import check_errors  # noqa: F401  (re-exported: networks_original.check_errors())
 
 PRECISIONS = {"fp32": 0, "3xtf32": 1, "tf32": 2}
 DEFAULT_PRECISION = "3xtf32"
@@ -151,9 +152,12 @@ class _NetBase:
 
     @staticmethod
     def _finish(out, keep_torch):
+        """numpy in -> numpy out like the reference's session.run (synchronises and checks the device error flag);
+        torch CUDA tensors in -> torch CUDA tensors out, asynchronous: call `check_errors()` after synchronising."""
         if keep_torch:
             return out
         torch.cuda.current_stream().synchronize()
+        _lib.check_errors()
         return {k: v.cpu().numpy() for k, v in out.items()}
 
 
@@ -179,11 +183,11 @@ class IterativeNet(_NetBase):
     def eval(self, image_pair, image2_2, depth2, normal2, rotation, translation):
         b, f = self.batch_size, self._fmt
         ip, t1 = _to_dev(image_pair, _shape(f, b, 6, 192, 256), "image_pair")
-        i2, _ = _to_dev(image2_2, _shape(f, b, 3, 48, 64), "image2_2")
-        d2, _ = _to_dev(depth2, _shape(f, b, 1, 48, 64), "depth2")
-        n2, _ = _to_dev(normal2, _shape(f, b, 3, 48, 64), "normal2")
-        r, _ = _to_dev(rotation, (b, 3), "rotation")
-        t, _ = _to_dev(translation, (b, 3), "translation")
+        i2, t2 = _to_dev(image2_2, _shape(f, b, 3, 48, 64), "image2_2")
+        d2, t3 = _to_dev(depth2, _shape(f, b, 1, 48, 64), "depth2")
+        n2, t4 = _to_dev(normal2, _shape(f, b, 3, 48, 64), "normal2")
+        r, t5 = _to_dev(rotation, (b, 3), "rotation")
+        t, t6 = _to_dev(translation, (b, 3), "translation")
         net = self.session.net(b)
         out = self._outputs(ip.device)
         _lib.check(_lib.load().demon_iterative_forward(
@@ -191,7 +195,7 @@ class IterativeNet(_NetBase):
             out["predict_flow5"].data_ptr(), out["predict_flow2"].data_ptr(), out["predict_depth2"].data_ptr(),
             out["predict_normal2"].data_ptr(), out["predict_rotation"].data_ptr(), out["predict_translation"].data_ptr(),
             f, _stream()))
-        return self._finish(out, t1)
+        return self._finish(out, t1 and t2 and t3 and t4 and t5 and t6)   # torch out only if every input was a CUDA tensor
 
 
 class RefinementNet(_NetBase):
@@ -208,12 +212,12 @@ class RefinementNet(_NetBase):
         b, f = self.batch_size, self._fmt
         H, W = self.image_size
         im, t1 = _to_dev(image1, _shape(f, b, 3, H, W), "image1")
-        d2, _ = _to_dev(depth2, _shape(f, b, 1, H // 4, W // 4), "depth2")
+        d2, t2 = _to_dev(depth2, _shape(f, b, 1, H // 4, W // 4), "depth2")
         net = self.session.net(b, (H, W))
         out = {"predict_depth0": torch.empty(_shape(f, b, 1, H, W), dtype=torch.float32, device=im.device)}
         _lib.check(_lib.load().demon_refine_forward(net.ptr, im.data_ptr(), d2.data_ptr(), out["predict_depth0"].data_ptr(),
                                                     f, _stream()))
-        return self._finish(out, t1)
+        return self._finish(out, t1 and t2)
 
 
 class DemonPipeline:
@@ -226,20 +230,39 @@ class DemonPipeline:
         # private_net: an own network handle (own workspace), so that two pipelines can be in flight on two streams
         self.net = (_NetHandle(self.session.weights, self.batch_size, (192, 256), self.session.precision) if private_net
                     else self.session.net(self.batch_size))
+        # The C call replays ONE CUDA graph per set of pointer arguments, so the pipeline owns persistent input staging
+        # and output buffers: the graph key is then the same for every call, whatever tensors the caller passes.
+        self._ip = self._i22 = self._out = None
 
-    def forward(self, image_pair, image2_2=None, outputs=None):
+    def forward(self, image_pair, image2_2=None, outputs=None, stage_inputs=True):
         """image_pair: torch CUDA [B,6,192,256]; image2_2: torch CUDA [B,3,48,64] or None (then it is
         median3x3_downsample applied twice to the second image, examples/evaluation.py:170-173).
-        Returns dict of torch CUDA tensors; no host synchronisation."""
+        Returns dict of torch CUDA tensors; no host synchronisation.  With `outputs=None` the result tensors belong to
+        the pipeline and are overwritten by the next call (clone them to keep them).  `stage_inputs=False` skips the
+        device-to-device copy into the pipeline's own input buffers; pass the same tensors every call then, or every
+        new pointer set costs an eager ~270-launch pass plus a graph capture."""
         b = self.batch_size
         ip, _ = _to_dev(image_pair, (b, 6, 192, 256), "image_pair")
         i2 = None
         if image2_2 is not None:
             i2, _ = _to_dev(image2_2, (b, 3, 48, 64), "image2_2")
+        if stage_inputs:
+            if self._ip is None:
+                self._ip = torch.empty((b, 6, 192, 256), dtype=torch.float32, device=ip.device)
+                self._i22 = torch.empty((b, 3, 48, 64), dtype=torch.float32, device=ip.device)
+            if ip.data_ptr() != self._ip.data_ptr():
+                self._ip.copy_(ip, non_blocking=True)
+            ip = self._ip
+            if i2 is not None:
+                if i2.data_ptr() != self._i22.data_ptr():
+                    self._i22.copy_(i2, non_blocking=True)
+                i2 = self._i22
         if outputs is None:
-            mk = lambda *s: torch.empty(s, dtype=torch.float32, device=ip.device)
-            outputs = {"predict_depth0": mk(b, 1, 192, 256), "predict_rotation": mk(b, 3), "predict_translation": mk(b, 3),
-                       "predict_flow2": mk(b, 2, 48, 64), "predict_depth2": mk(b, 1, 48, 64), "predict_normal2": mk(b, 3, 48, 64)}
+            if self._out is None:
+                mk = lambda *s: torch.empty(s, dtype=torch.float32, device=ip.device)
+                self._out = {"predict_depth0": mk(b, 1, 192, 256), "predict_rotation": mk(b, 3), "predict_translation": mk(b, 3),
+                             "predict_flow2": mk(b, 2, 48, 64), "predict_depth2": mk(b, 1, 48, 64), "predict_normal2": mk(b, 3, 48, 64)}
+            outputs = self._out
         ptr = lambda k: outputs[k].data_ptr() if outputs.get(k) is not None else None
         _lib.check(_lib.load().demon_pipeline_forward(
             self.net.ptr, ip.data_ptr(), None if i2 is None else i2.data_ptr(), self.iterations,
@@ -256,6 +279,7 @@ class DemonPipeline:
             return x.data_ptr() if isinstance(x, torch.Tensor) else x.ctypes.data
         _lib.check(_lib.load().demon_pipeline_forward_host(
             self.net.ptr, hp(image_pair), hp(image2_2), self.iterations, hp(depth0), hp(rotation), hp(translation), _stream()))
+        # (the C call synchronises and returns DEMON_E_STATE itself if a tcgen05 pipeline wait timed out)
 
     def forward_host_async(self, image_pair, image2_2, depth0, rotation, translation, stream=None):
         """forward_host without the final synchronisation, on `stream` (a torch.cuda.Stream; default: current).  The host

@@ -185,11 +185,26 @@ const char* demon_net_layer_name(const demon_net* net, int i);
 int demon_net_layer_profile(const demon_net* net, int i, double* ms, int64_t* calls, int* launches_per_call,
                             int* uses_tc);
 
-/* 1 if a pipeline wait inside the tcgen05 kernel ever timed out in this process (synchronises the device). */
+/* 1 if a pipeline wait inside a tcgen05 kernel has timed out on the current device since the flag was last
+ * cleared (synchronises the device; does not clear). */
 int demon_debug_tc_timeouts(void);
+/* Synchronises the current device and returns DEMON_E_STATE if a bounded pipeline wait inside a tcgen05 convolution
+ * kernel timed out since the last check (such a kernel runs to completion with garbage instead of hanging the GPU),
+ * DEMON_E_CUDA for a pending CUDA error, DEMON_OK otherwise.  Clears the flag.  The `_host` entry points that
+ * synchronise call it themselves; callers of the asynchronous / device-pointer entry points call it after their own
+ * synchronisation (replaces the `throw std::runtime_error` of _CHECK_CUDA_ERROR, lmbspecialops/src/cuda_helper.h:25-35). */
+int demon_check_errors(void);
 /* debug: host_out == NULL: switch the halo kernel's per-CTA wait-cycle counters on/off; otherwise copy [nblocks][16]
  * counters of the last launch to host_out. */
 int demon_debug_tc_timing(int enable, int64_t* host_out, int nblocks);
+
+/* debug: one text line per layer with the kernel family and tiling plan it gets (works without a device as long as the
+ * net was created -- creation needs one; see tools/describe_plan.py for the offline variant). Returns bytes written. */
+int demon_debug_describe_layers(const demon_net* net, char* buf, int buflen);
+
+/* debug, no device needed: the kernel family and tiling plan one convolution shape would get */
+int demon_debug_describe_conv(int B, int H, int W, int Cin, int in_pitch, int Cout, int out_pitch, int kh, int kw, int sy, int sx,
+                              int deconv, int precision, char* buf, int buflen);
 
 /* Standalone convolution entry used by tests to compare the tcgen05 path with the fp32 SIMT path on
  * the same NHWC tensors.  in [B,H,W,Cin], kernel TF layout [kh,kw,cin,cout] (host), bias [cout] (host)

@@ -134,10 +134,6 @@ TC_CASES = [
 ]
 
 
-def tc_available():
-    return True
-
-
 @pytest.mark.parametrize("case", TC_CASES)
 def test_tc_conv_3xtf32_is_fp32_grade(case):
     B, H, W, Cin, Cout, kh, kw, sy, sx = case
@@ -160,7 +156,13 @@ def test_tc_conv_3xtf32_is_fp32_grade(case):
     assert _lib.load().demon_debug_tc_timeouts() == 0
 
 
-@pytest.mark.parametrize("case", [(2, 6, 8, 512, 256), (1, 12, 16, 256, 128), (1, 24, 32, 128, 32), (2, 12, 16, 128, 64)])
+# transposed convs: per-tap mode at low resolution (refine4/3/2 shapes, 17 chunks for the 544-channel concat), halo mode
+# on whole 16x8 tiles (refine0: four stacked classes of N = 32; refine1: four classes of N = 64, three-instruction mode)
+TC_DECONV_CASES = [(2, 6, 8, 512, 256), (1, 12, 16, 256, 128), (1, 24, 32, 128, 32), (2, 12, 16, 128, 64), (1, 12, 16, 544, 128),
+                   (3, 24, 32, 256, 64), (1, 32, 16, 128, 32), (2, 16, 24, 128, 64), (1, 16, 8, 32, 16)]
+
+
+@pytest.mark.parametrize("case", TC_DECONV_CASES)
 def test_tc_deconv_3xtf32_is_fp32_grade(case):
     B, H, W, Cin, Cout = case
     rng = np.random.RandomState(sum(case) + 2)
@@ -174,3 +176,6 @@ def test_tc_deconv_3xtf32_is_fp32_grade(case):
     ref = ref_deconv(x, k, b, True)
     assert got.shape == ref.shape and not np.isnan(got).any()
     assert rel_err(got, ref) < 2e-5, rel_err(got, ref)
+    got1 = run_deconv(x, k, b, True, TF32)
+    assert rel_err(got1, ref) < 5e-3
+    assert _lib.load().demon_debug_tc_timeouts() == 0

@@ -113,7 +113,8 @@ def main():
             print("pipeline timeout flagged -- stopping")
             return
     for name, B, H, W, Cin, Cout in [("HALO deconv 16x8 Cin32 Cout32", 1, 16, 8, 32, 32), ("HALO deconv 48x64 Cin128 Cout64", 2, 48, 64, 128, 64),
-                                     ("HALO deconv 32x32 Cin128 Cout32", 1, 32, 32, 128, 32), ("v1 deconv 24x32 Cin256 Cout64", 2, 24, 32, 256, 64)]:
+                                     ("HALO deconv 32x32 Cin128 Cout32", 1, 32, 32, 128, 32), ("per-tap deconv 24x32 Cin256 Cout64", 2, 24, 32, 256, 64),
+                                     ("per-tap deconv 12x16 Cin544 Cout128", 1, 12, 16, 544, 128), ("per-tap deconv 6x8 Cin512 Cout256", 2, 6, 8, 512, 256)]:
         x = rng.uniform(-1, 1, (B, H, W, Cin)).astype(np.float32)
         k = (rng.standard_normal((4, 4, Cout, Cin)) / np.sqrt(4 * Cin)).astype(np.float32)
         b = rng.uniform(-0.1, 0.1, Cout).astype(np.float32)
