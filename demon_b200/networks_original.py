@@ -82,7 +82,14 @@ class Session:
         self.weights = weights
         self._nets = {}
 
-    restore = load_weights
+    def restore(self, save_path):
+        """`tf.train.Saver().restore(session, save_path)` of examples/example.py:82-83: reads the TensorFlow checkpoint
+        `save_path` (prefix of the .index / .data-0000x-of-0000y files, e.g. 'weights/demon_original') with the
+        pure-Python bundle reader.  A dict of arrays is accepted as well (same as load_weights)."""
+        if isinstance(save_path, dict):
+            return self.load_weights(save_path)
+        from . import checkpoint
+        self.load_weights(checkpoint.load_demon_weights(str(save_path)))
 
     def net(self, batch, refine_hw=(192, 256)):
         if self.weights is None:
@@ -234,6 +241,32 @@ class DemonPipeline:
         # and output buffers: the graph key is then the same for every call, whatever tensors the caller passes.
         self._ip = self._i22 = self._out = None
 
+    def stage(self, image_pair, image2_2=None):
+        """Copies the inputs into the pipeline's own device buffers (asynchronous, current stream) and returns them."""
+        b = self.batch_size
+        ip, _ = _to_dev(image_pair, (b, 6, 192, 256), "image_pair")
+        if self._ip is None:
+            self._ip = torch.empty((b, 6, 192, 256), dtype=torch.float32, device=ip.device)
+            self._i22 = torch.empty((b, 3, 48, 64), dtype=torch.float32, device=ip.device)
+        if ip.data_ptr() != self._ip.data_ptr():
+            self._ip.copy_(ip, non_blocking=True)
+        i2 = None
+        if image2_2 is not None:
+            i2, _ = _to_dev(image2_2, (b, 3, 48, 64), "image2_2")
+            if i2.data_ptr() != self._i22.data_ptr():
+                self._i22.copy_(i2, non_blocking=True)
+            i2 = self._i22
+        return self._ip, i2
+
+    def own_outputs(self):
+        if self._out is None:
+            b = self.batch_size
+            dev = self._ip.device if self._ip is not None else torch.device("cuda", torch.cuda.current_device())
+            mk = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+            self._out = {"predict_depth0": mk(b, 1, 192, 256), "predict_rotation": mk(b, 3), "predict_translation": mk(b, 3),
+                         "predict_flow2": mk(b, 2, 48, 64), "predict_depth2": mk(b, 1, 48, 64), "predict_normal2": mk(b, 3, 48, 64)}
+        return self._out
+
     def forward(self, image_pair, image2_2=None, outputs=None, stage_inputs=True):
         """image_pair: torch CUDA [B,6,192,256]; image2_2: torch CUDA [B,3,48,64] or None (then it is
         median3x3_downsample applied twice to the second image, examples/evaluation.py:170-173).
@@ -242,27 +275,25 @@ class DemonPipeline:
         device-to-device copy into the pipeline's own input buffers; pass the same tensors every call then, or every
         new pointer set costs an eager ~270-launch pass plus a graph capture."""
         b = self.batch_size
-        ip, _ = _to_dev(image_pair, (b, 6, 192, 256), "image_pair")
-        i2 = None
-        if image2_2 is not None:
-            i2, _ = _to_dev(image2_2, (b, 3, 48, 64), "image2_2")
         if stage_inputs:
+            ip, i2 = self.stage(image_pair, image2_2)
+        else:
+            ip, _ = _to_dev(image_pair, (b, 6, 192, 256), "image_pair")
+            i2 = None
+            if image2_2 is not None:
+                i2, _ = _to_dev(image2_2, (b, 3, 48, 64), "image2_2")
+        return self.forward_staged(outputs, ip, i2)
+
+    def forward_staged(self, outputs=None, ip=None, i2=None, use_image2_2=False):
+        """The pipeline on inputs that are already in place: by default the pipeline's own staging buffers (filled by
+        `stage()`; image2_2 only if `use_image2_2`).  This is the part a caller captures in a CUDA graph of its own
+        (bench.py captures it together with the all-gather that follows)."""
+        if ip is None:
             if self._ip is None:
-                self._ip = torch.empty((b, 6, 192, 256), dtype=torch.float32, device=ip.device)
-                self._i22 = torch.empty((b, 3, 48, 64), dtype=torch.float32, device=ip.device)
-            if ip.data_ptr() != self._ip.data_ptr():
-                self._ip.copy_(ip, non_blocking=True)
-            ip = self._ip
-            if i2 is not None:
-                if i2.data_ptr() != self._i22.data_ptr():
-                    self._i22.copy_(i2, non_blocking=True)
-                i2 = self._i22
+                raise RuntimeError("forward_staged() before stage()")
+            ip, i2 = self._ip, (self._i22 if use_image2_2 else None)
         if outputs is None:
-            if self._out is None:
-                mk = lambda *s: torch.empty(s, dtype=torch.float32, device=ip.device)
-                self._out = {"predict_depth0": mk(b, 1, 192, 256), "predict_rotation": mk(b, 3), "predict_translation": mk(b, 3),
-                             "predict_flow2": mk(b, 2, 48, 64), "predict_depth2": mk(b, 1, 48, 64), "predict_normal2": mk(b, 3, 48, 64)}
-            outputs = self._out
+            outputs = self.own_outputs()
         ptr = lambda k: outputs[k].data_ptr() if outputs.get(k) is not None else None
         _lib.check(_lib.load().demon_pipeline_forward(
             self.net.ptr, ip.data_ptr(), None if i2 is None else i2.data_ptr(), self.iterations,

@@ -1,7 +1,7 @@
 """Multi-GPU plumbing of the DeMoN inference path: image pairs are independent
 (blocks_original.py has no cross-sample op; `predicted_scale` is per sample, blocks_original.py:281-283),
 so a batch shards by contiguous ranges over one process per GPU and the only exchange is ONE all-gather
-of the final depth / motion tensors.  The reference has no distributed code at all.
+(one NCCL call per step) of the final depth / motion tensors.  The reference has no distributed code at all.
 
 Works on the `nccl` backend (CUDA tensors, the product path) and on `gloo` (CPU tensors, used by the
 world_size-2 tests of this host logic)."""
@@ -38,26 +38,51 @@ def init_from_env(backend=None):
 
 
 class OutputGather:
-    """The single collective of the path: all-gather of depth0 [b,1,H,W] and motion (rotation|translation)
-    [b,6] of equal-sized shards into preallocated global buffers, launched on the current stream."""
+    """The single collective of the path: ONE all-gather per step of every rank's final predictions.
+
+    A rank's record is one contiguous buffer [depth0 (b x H x W) | rotation (b x 3) | translation (b x 3)];
+    `local_buffers()` hands out views into it so that the pipeline writes its results straight into the send buffer
+    (no staging copies), and `__call__()` is one `all_gather_into_tensor` on the current stream -- capturable in a CUDA
+    graph together with the pipeline that precedes it.  Shards must be equal (BASELINE.json configs[3]: 512 pairs over
+    8 GPUs = 64 per rank); `shard_range` can produce ragged shards for other uses, this class refuses them.
+    Results: `depth_all` [world, b, 1, H, W], `rotation_all` / `translation_all` [world, b, 3] (views, rank-major = the
+    global batch order of `shard_range`); `gathered()` returns them reshaped to the global batch (copies)."""
 
     def __init__(self, shard_batch, world_size, hw=(192, 256), device="cuda"):
-        self.world = world_size
-        self.shard = shard_batch
-        self.depth_all = torch.empty((world_size * shard_batch, 1) + tuple(hw), dtype=torch.float32, device=device)
-        self.motion = torch.empty((shard_batch, 6), dtype=torch.float32, device=device)
-        self.motion_all = torch.empty((world_size * shard_batch, 6), dtype=torch.float32, device=device)
+        self.world = int(world_size)
+        self.shard = int(shard_batch)
+        self.hw = tuple(hw)
+        b, n = self.shard, self.hw[0] * self.hw[1]
+        self.record = b * (n + 6)
+        self.local = torch.empty(self.record, dtype=torch.float32, device=device)
+        self.flat_all = self.local if self.world == 1 else torch.empty(self.world * self.record, dtype=torch.float32, device=device)
+        self.all = self.flat_all.view(self.world, self.record)
+        self.depth_all = self.all[:, :b * n].unflatten(1, (b, 1) + self.hw)
+        self.rotation_all = self.all[:, b * n:b * n + 3 * b].unflatten(1, (b, 3))
+        self.translation_all = self.all[:, b * n + 3 * b:].unflatten(1, (b, 3))
 
-    def __call__(self, depth0, rotation, translation):
-        self.motion[:, 0:3].copy_(rotation)
-        self.motion[:, 3:6].copy_(translation)
-        if self.world == 1:
-            self.depth_all.copy_(depth0)
-            self.motion_all.copy_(self.motion)
-        else:
-            dist.all_gather_into_tensor(self.depth_all, depth0.contiguous())
-            dist.all_gather_into_tensor(self.motion_all, self.motion)
-        return self.depth_all, self.motion_all
+    def local_buffers(self):
+        """(depth0 [b,1,H,W], rotation [b,3], translation [b,3]): views into this rank's send buffer."""
+        b, n = self.shard, self.hw[0] * self.hw[1]
+        return (self.local[:b * n].view((b, 1) + self.hw), self.local[b * n:b * n + 3 * b].view(b, 3), self.local[b * n + 3 * b:].view(b, 3))
+
+    def __call__(self, depth0=None, rotation=None, translation=None):
+        """Gathers the local record.  Tensors that are not the `local_buffers()` views are copied in first."""
+        d, r, t = self.local_buffers()
+        for src, dst in ((depth0, d), (rotation, r), (translation, t)):
+            if src is not None and src.data_ptr() != dst.data_ptr():
+                if tuple(src.shape) != tuple(dst.shape):
+                    raise ValueError("OutputGather: shard of shape %s, expected %s (shards must be equal)" % (tuple(src.shape), tuple(dst.shape)))
+                dst.copy_(src)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.flat_all, self.local)
+        return self.depth_all, self.rotation_all, self.translation_all
+
+    def gathered(self):
+        """(depth [world*b,1,H,W], motion [world*b,6]) of the last call, in global batch order (copies)."""
+        wb = self.world * self.shard
+        motion = torch.cat([self.rotation_all.reshape(wb, 3), self.translation_all.reshape(wb, 3)], dim=1)
+        return self.depth_all.reshape((wb, 1) + self.hw), motion
 
 
 def max_over_ranks(value, device):

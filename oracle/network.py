@@ -5,8 +5,7 @@ PARITY UNPINNED at the network level: the reference holds no test, golden
 output or checkpoint for its TensorFlow graphs, and
 TensorFlow 1.4 cannot be installed here.  What pins this file is (a) the
 line-by-line restatement below, every function citing the reference, and (b)
-tests/test_oracle_network.py (test_torch_conv_equals_tf_definition and
-following), which checks the torch calls used here against naive numpy loops
+tests/test_oracle_network.py (test_*_matches_tf_definition), which checks the torch calls used here against naive numpy loops
 written directly from TensorFlow's documented definitions of conv2d /
 conv2d_transpose / dense / resize_nearest_neighbor.  The geometry ops this
 file threads between the blocks (oracle/ops.py) ARE pinned: bit for bit against

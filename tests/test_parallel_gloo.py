@@ -42,8 +42,21 @@ def _worker(rank, world, port, B, out_q):
     full_depth = torch.rand(B, 1, 6, 8, generator=g)
     full_motion = torch.rand(B, 6, generator=g)
     gather = parallel.OutputGather(end - begin, world, hw=(6, 8), device="cpu")
-    d_all, m_all = gather(full_depth[begin:end], full_motion[begin:end, 0:3], full_motion[begin:end, 3:6])
+    # first through copies, then with the "pipeline" writing straight into the send buffer views
+    gather(full_depth[begin:end], full_motion[begin:end, 0:3], full_motion[begin:end, 3:6])
+    d_all, m_all = gather.gathered()
     ok = torch.equal(d_all, full_depth) and torch.equal(m_all, full_motion)
+    d, r, t = gather.local_buffers()
+    d.copy_(2 * full_depth[begin:end]); r.copy_(full_motion[begin:end, 0:3]); t.copy_(-full_motion[begin:end, 3:6])
+    gather()
+    d_all, m_all = gather.gathered()
+    ok = ok and torch.equal(d_all, 2 * full_depth) and torch.equal(m_all[:, :3], full_motion[:, :3]) and torch.equal(m_all[:, 3:], -full_motion[:, 3:])
+    ok = ok and gather.depth_all.shape == (world, end - begin, 1, 6, 8)
+    try:
+        gather(full_depth[:1], None, None)
+        ok = False
+    except ValueError:
+        pass
     t = parallel.max_over_ranks(1.0 + rank, "cpu")
     out_q.put((rank, ok, t))
     dist.barrier()
