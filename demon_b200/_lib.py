@@ -40,6 +40,9 @@ PROTOTYPES = {
     "demon_pipeline_forward": [_P, _P, _P, c_int] + [_P] * 6 + [_P],
     "demon_pipeline_forward_host": [_P, _P, _P, c_int, _P, _P, _P, _P],
     "demon_pipeline_forward_host_async": [_P, _P, _P, c_int, _P, _P, _P, _P],
+    "demon_pipeline_forward_u8": [_P, _P, _P, c_int] + [_P] * 6 + [_P],
+    "demon_pipeline_forward_host_u8": [_P, _P, _P, c_int, _P, _P, _P, _P],
+    "demon_pipeline_forward_host_u8_async": [_P, _P, _P, c_int, _P, _P, _P, _P],
     "demon_net_batch": [_P],
     "demon_net_workspace_bytes": [_P],
     "demon_net_pipeline_launches": [_P, c_int],

@@ -83,6 +83,69 @@ __global__ void __launch_bounds__(128) warp2d_kernel(const T* __restrict__ in, c
   }
 }
 
+// float fast path: FOUR pixels per thread.  The displacement rows are read as two float4, the results of every channel
+// are stored as one float4, the index arithmetic is 32 bit (the launcher takes this path only while all tensors have
+// fewer than 2^31 elements, W is a multiple of 4 and the base pointers are 16-byte aligned), and the sixteen gathers of
+// a channel are in flight before the first blend.  Per-pixel arithmetic is the same sequence of IEEE operations as in
+// warp2d_kernel (bit exact with the reference's CPU kernel, warp2d.cc:186-247).
+template <bool CLAMP>
+__global__ void __launch_bounds__(128) warp2d_v4_kernel(const float* __restrict__ in, const float* __restrict__ disp,
+                                                       float* __restrict__ out, int C, int H, int W, bool normalized, float border_value) {
+  const int x = (blockIdx.x * 128 + threadIdx.x) * 4;
+  const int y = blockIdx.y;
+  const int n = blockIdx.z;
+  if (x >= W) return;
+  const int hw = H * W;
+  const int row = y * W + x;
+  const float* d = disp + n * 2 * hw + row;
+  const float4 dx = __ldg(reinterpret_cast<const float4*>(d));
+  const float4 dy = __ldg(reinterpret_cast<const float4*>(d + hw));
+  const float vx[4] = {dx.x, dx.y, dx.z, dx.w}, vy[4] = {dy.x, dy.y, dy.z, dy.w};
+  WarpTap<float> t[4];
+  int o00[4], o01[4], o10[4], o11[4];
+  bool valid[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    t[k] = warp2d_tap<float>(x + k, y, vx[k], vy[k], W, H, normalized);
+    if (CLAMP) {
+      const int x1i = (int)((unsigned)t[k].x0 + 1u), y1i = (int)((unsigned)t[k].y0 + 1u);
+      const int x0 = clampi(t[k].x0, W), x1 = clampi(x1i, W), y0 = clampi(t[k].y0, H), y1 = clampi(y1i, H);
+      o00[k] = y0 * W + x0; o01[k] = y0 * W + x1; o10[k] = y1 * W + x0; o11[k] = y1 * W + x1;
+      valid[k] = true;
+    } else {
+      valid[k] = warp2d_valid(t[k].x0, t[k].y0, W, H);
+      const int o = valid[k] ? t[k].y0 * W + t[k].x0 : 0;
+      o00[k] = o; o01[k] = o + 1; o10[k] = o + W; o11[k] = o + W + 1;
+    }
+  }
+  const float* src = in + n * C * hw;
+  float* dst = out + n * C * hw + row;
+  for (int c = 0; c < C; ++c, src += hw, dst += hw) {
+    float v[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (CLAMP || valid[k]) { v[k][0] = __ldg(src + o00[k]); v[k][1] = __ldg(src + o01[k]); v[k][2] = __ldg(src + o10[k]); v[k][3] = __ldg(src + o11[k]); }
+    float r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r[k] = (CLAMP || valid[k]) ? warp2d_blend(v[k][0], v[k][1], v[k][2], v[k][3], t[k]) : border_value;
+    *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+template <class T>
+static bool warp2d_fast(const T*, const T*, T*, int, int, int, int, int, int, T, cudaStream_t) { return false; }
+template <>
+bool warp2d_fast<float>(const float* in, const float* disp, float* out, int n, int c, int h, int w, int normalized, int border_mode,
+                        float border_value, cudaStream_t s) {
+  const int64_t total = (int64_t)n * (c > 2 ? c : 2) * h * w;
+  if ((w & 3) != 0 || w < 128 || total >= (1ll << 31) || ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(disp) | reinterpret_cast<uintptr_t>(out)) & 15) != 0)
+    return false;
+  dim3 grid(ceil_div(w / 4, 128), h, n), block(128);
+  if (border_mode == DEMON_BORDER_CLAMP) warp2d_v4_kernel<true><<<grid, block, 0, s>>>(in, disp, out, c, h, w, normalized != 0, border_value);
+  else warp2d_v4_kernel<false><<<grid, block, 0, s>>>(in, disp, out, c, h, w, normalized != 0, border_value);
+  return true;
+}
+
 template <class T>
 static int warp2d_launch(const T* in, const T* disp, T* out, int n, int c, int h, int w, int normalized,
                          int border_mode, T border_value, void* stream) {
@@ -93,6 +156,10 @@ static int warp2d_launch(const T* in, const T* disp, T* out, int n, int c, int h
   DEMON_REQUIRE(h <= 65535 && n <= 65535, "warp2d: h and n must be <= 65535");
   dim3 grid(ceil_div(w, 128), h, n), block(128);
   cudaStream_t s = (cudaStream_t)stream;
+  if (warp2d_fast<T>(in, disp, out, n, c, h, w, normalized, border_mode, border_value, s)) {
+    DEMON_LAUNCH_CHECK();
+    return DEMON_OK;
+  }
   if (border_mode == DEMON_BORDER_CLAMP)
     warp2d_kernel<T, true><<<grid, block, 0, s>>>(in, disp, out, c, h, w, normalized != 0, border_value);
   else
@@ -140,6 +207,50 @@ __global__ void __launch_bounds__(256) depth_to_flow_kernel(const T* __restrict_
   }
 }
 
+// float fast path: 2 x 4 consecutive pixels per thread, float4 loads and stores, 32-bit indices (H*W a multiple of 4 with W a
+// multiple of 4 so that a group never crosses a row; fewer than 2^31 elements; 16-byte aligned pointers)
+__global__ void __launch_bounds__(256) depth_to_flow_v4_kernel(const float* __restrict__ depth, const float* __restrict__ intrinsics,
+                                                              const float* __restrict__ rotation, const float* __restrict__ translation,
+                                                              float* __restrict__ flow, int H, int W, int rotation_format,
+                                                              bool inverse_depth, bool normalize_flow) {
+  __shared__ D2FCamera<float> cam;
+  const int n = blockIdx.y;
+  if (threadIdx.x == 0)
+    d2f_camera(cam, intrinsics + 4 * n, rotation + (size_t)n * rotation_step(rotation_format), translation + 3 * n, rotation_format, W, H);
+  __syncthreads();
+  const int hw = H * W;
+  const float* dn = depth + n * hw;
+  float* fn = flow + n * 2 * hw;
+  float4 dv[2];
+  int idx[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    idx[k] = ((blockIdx.x * 2 + k) * 256 + threadIdx.x) * 4;
+    dv[k] = (idx[k] < hw) ? __ldg(reinterpret_cast<const float4*>(dn + idx[k])) : make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (idx[k] >= hw) continue;
+    const int y = idx[k] / W, x = idx[k] - y * W;
+    const float d4[4] = {dv[k].x, dv[k].y, dv[k].z, dv[k].w};
+    float fx[4], fy[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d2f_pixel(fx[j], fy[j], d4[j], x + j, y, cam, inverse_depth, normalize_flow);
+    *reinterpret_cast<float4*>(fn + idx[k]) = make_float4(fx[0], fx[1], fx[2], fx[3]);
+    *reinterpret_cast<float4*>(fn + hw + idx[k]) = make_float4(fy[0], fy[1], fy[2], fy[3]);
+  }
+}
+
+template <class T>
+static bool d2f_fast(const T*, const T*, const T*, const T*, T*, int, int, int, int, int, int, cudaStream_t) { return false; }
+template <>
+bool d2f_fast<float>(const float* depth, const float* k, const float* r, const float* t, float* flow, int n, int h, int w, int rf, int inv,
+                     int nrm, cudaStream_t s) {
+  if ((w & 3) != 0 || (int64_t)n * 2 * h * w >= (1ll << 31) || ((reinterpret_cast<uintptr_t>(depth) | reinterpret_cast<uintptr_t>(flow)) & 15) != 0) return false;
+  depth_to_flow_v4_kernel<<<dim3(ceil_div(h * w, 256 * 8), n), 256, 0, s>>>(depth, k, r, t, flow, h, w, rf, inv != 0, nrm != 0);
+  return true;
+}
+
 template <class T>
 static int depth_to_flow_launch(const T* depth, const T* intrinsics, const T* rotation, const T* translation, T* flow,
                                 int n, int h, int w, int rotation_format, int inverse_depth, int normalize_flow, void* stream) {
@@ -147,6 +258,10 @@ static int depth_to_flow_launch(const T* depth, const T* intrinsics, const T* ro
   DEMON_REQUIRE(n >= 0 && h >= 0 && w >= 0 && n <= 65535, "depth_to_flow: bad size");
   if ((int64_t)n * h * w == 0) return DEMON_OK;
   DEMON_REQUIRE(depth && intrinsics && rotation && translation && flow, "depth_to_flow: null pointer");
+  if (d2f_fast<T>(depth, intrinsics, rotation, translation, flow, n, h, w, rotation_format, inverse_depth, normalize_flow, (cudaStream_t)stream)) {
+    DEMON_LAUNCH_CHECK();
+    return DEMON_OK;
+  }
   depth_to_flow_kernel<T><<<dim3(ceil_div(h * w, 256 * kPixPerThread), n), 256, 0, (cudaStream_t)stream>>>(
       depth, intrinsics, rotation, translation, flow, h, w, rotation_format, inverse_depth != 0, normalize_flow != 0);
   DEMON_LAUNCH_CHECK();
@@ -267,6 +382,49 @@ __global__ void __launch_bounds__(128) median3x3_downsample_kernel(const T* __re
   out[z * Ho * Wo + (size_t)yo * Wo + xo] = median9_reference_order(v);
 }
 
+// float fast path: FOUR outputs per thread.  Of each of the three (clamped) input rows the thread reads the eight columns
+// 2*xo .. 2*xo+7 as two float4 plus the one column to the left; the four windows share these 27 values, and the result is
+// one float4 store.  Taken when W is a multiple of 8 (then Wo is a multiple of 4, every group is complete and all vector
+// accesses are aligned) with 16-byte aligned pointers and fewer than 2^31 elements.  The selection network is the
+// reference's, compare for compare (median9_reference_order).
+__global__ void __launch_bounds__(128) median3x3_v4_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int Ho, int Wo,
+                                                          int zbase) {
+  const int xo = (blockIdx.x * 128 + threadIdx.x) * 4;
+  const int yo = blockIdx.y;
+  const int z = zbase + blockIdx.z;
+  if (xo >= Wo) return;
+  const float* p = in + z * (H * W);
+  const int x = 2 * xo, y = 2 * yo;
+  float r[3][9];   // columns x-1 .. x+7 of rows y-1, y, y+1
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const float* q = p + clampi(y + dy - 1, H) * W + x;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(q)), b = __ldg(reinterpret_cast<const float4*>(q + 4));
+    r[dy][0] = __ldg(q - (x > 0 ? 1 : 0));
+    r[dy][1] = a.x; r[dy][2] = a.y; r[dy][3] = a.z; r[dy][4] = a.w;
+    r[dy][5] = b.x; r[dy][6] = b.y; r[dy][7] = b.z; r[dy][8] = b.w;
+  }
+  float m[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float v[9];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) v[3 * dy + dx] = r[dy][2 * j + dx];
+    m[j] = median9_reference_order(v);
+  }
+  *reinterpret_cast<float4*>(out + z * (Ho * Wo) + yo * Wo + xo) = make_float4(m[0], m[1], m[2], m[3]);
+}
+
+template <class T>
+static bool median_fast(const T*, T*, int, int, int, int, int, int, cudaStream_t) { return false; }
+template <>
+bool median_fast<float>(const float* in, float* out, int h, int w, int ho, int wo, int z0, int zn, cudaStream_t s) {
+  median3x3_v4_kernel<<<dim3(ceil_div(wo / 4, 128), ho, zn), 128, 0, s>>>(in, out, h, w, ho, wo, z0);
+  return true;
+}
+
 template <class T>
 static int median3x3_launch(const T* in, T* out, int64_t z, int h, int w, void* stream) {
   DEMON_REQUIRE(z >= 0 && h >= 0 && w >= 0, "median3x3_downsample: negative size");
@@ -274,8 +432,15 @@ static int median3x3_launch(const T* in, T* out, int64_t z, int h, int w, void* 
   DEMON_REQUIRE(in && out, "median3x3_downsample: null pointer");
   const int ho = (h + 1) / 2, wo = (w + 1) / 2;
   DEMON_REQUIRE(ho <= 65535, "median3x3_downsample: height too large");
+  // (the last column 2*xo+7 <= W-1 needs no clamp when W is a multiple of 8)
+  const bool fast = sizeof(T) == 4 && (w & 7) == 0 && w >= 256 && z * h * w < (1ll << 31) &&
+                    ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
   for (int64_t z0 = 0; z0 < z; z0 += 32768) {
     int zn = (int)((z - z0 < 32768) ? (z - z0) : 32768);
+    if (fast && median_fast<T>(in, out, h, w, ho, wo, (int)z0, zn, (cudaStream_t)stream)) {
+      DEMON_LAUNCH_CHECK();
+      continue;
+    }
     median3x3_downsample_kernel<T><<<dim3(ceil_div(wo, 128), ho, zn), 128, 0, (cudaStream_t)stream>>>(in, out, h, w, ho, wo, (int)z0);
     DEMON_LAUNCH_CHECK();
   }

@@ -574,6 +574,44 @@ __global__ void __launch_bounds__(256) refine_input_kernel(const float* __restri
   }
 }
 
+// uint8 input (examples/example.py:15-42: PIL RGB images, `np.array(img).astype(np.float32)/255 - 0.5`, pair concat):
+// images [B,2,H,W,3] uint8 -> img8 [B,H,W,8] fp32 = [image1 rgb, image2 rgb, 0, 0] (the conv1y input) and the NCHW
+// fp32 planes of image 2 (input of the median3x3 pair that makes image2_2, examples/evaluation.py:170-173).
+// Same two IEEE operations as numpy's float32 expression, so the result equals the fp32 entry bit for bit.
+__global__ void __launch_bounds__(256) u8_import_kernel(const unsigned char* __restrict__ images, float* __restrict__ img8,
+                                                       float* __restrict__ planes2, int B, int P) {
+  const long total = (long)B * P;
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const int n = (int)(i / P), p = (int)(i - (long)n * P);
+    const unsigned char* a = images + ((long)n * 2 * P + p) * 3;
+    const unsigned char* b = a + (long)P * 3;
+    float v[6];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      v[c] = fsub(fdiv((float)a[c], 255.0f), 0.5f);
+      v[3 + c] = fsub(fdiv((float)b[c], 255.0f), 0.5f);
+    }
+    reinterpret_cast<float4*>(img8)[2 * i] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(img8)[2 * i + 1] = make_float4(v[4], v[5], 0.f, 0.f);
+    if (planes2) {
+      float* q = planes2 + (long)n * 3 * P + p;
+      q[0] = v[3]; q[P] = v[4]; q[2L * P] = v[5];
+    }
+  }
+}
+
+// image2_2 given as uint8 [B,h,w,3] (examples/example.py:22: the PIL-resized second image) -> NCHW fp32 planes
+__global__ void __launch_bounds__(256) u8_planes_kernel(const unsigned char* __restrict__ img, float* __restrict__ planes, int B, int P) {
+  const long total = (long)B * P;
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const int n = (int)(i / P), p = (int)(i - (long)n * P);
+    const unsigned char* a = img + i * 3;
+    float* q = planes + (long)n * 3 * P + p;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) q[(long)c * P] = fsub(fdiv((float)a[c], 255.0f), 0.5f);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward passes
 // ---------------------------------------------------------------------------------------------
@@ -592,10 +630,10 @@ int import_image2_2(demon_net* n, const float* image2_2, int data_format, cudaSt
   return strided_copy(image2_2, n->i22->p, n->B, P, 3, 3L * P, 3, 1, 3L * P, 1, P, s);
 }
 
-int median_image2_2(demon_net* n, const float* image_pair_nchw, cudaStream_t s) {
+// planes: image 2 as NCHW fp32 planes, `sn` floats between samples (6*P inside an image pair, 3*P for a packed copy)
+int median_image2_2(demon_net* n, const float* planes, long sn, cudaStream_t s) {
   const int B = n->B;
-  median_planes_kernel<<<dim3(1, 96, B * 3), 128, 0, s>>>(image_pair_nchw + 3L * 192 * 256, n->i22_half->p, 3, 192, 256, 96, 128,
-                                                         6L * 192 * 256, 3L * 96 * 128);
+  median_planes_kernel<<<dim3(1, 96, B * 3), 128, 0, s>>>(planes, n->i22_half->p, 3, 192, 256, 96, 128, sn, 3L * 96 * 128);
   DEMON_LAUNCH_CHECK();
   median_planes_kernel<<<dim3(1, 48, B * 3), 128, 0, s>>>(n->i22_half->p, n->i22->p, 3, 96, 128, 48, 64, 3L * 96 * 128, 3L * 48 * 64);
   DEMON_LAUNCH_CHECK();
@@ -919,14 +957,40 @@ int demon_refine_forward(demon_net* n, const float* image1, const float* depth2,
   return run_refine_block(n, image1, 3 * P, 3, 1, depth2, (long)dh * dw, 1, dh, dw, depth0, (cudaStream_t)stream);
 }
 
-static int pipeline_body(demon_net* n, const float* image_pair, const float* image2_2, int iterations, float* depth0, float* rotation,
+// Input of the fused pipeline: fp32 NCHW (image_pair [B,6,192,256], image2_2 [B,3,48,64] or null) or uint8
+// (images [B,2,192,256,3], image2_2 [B,48,64,3] or null).
+struct PipelineInput {
+  const float* image_pair = nullptr;
+  const float* image2_2 = nullptr;
+  const unsigned char* images_u8 = nullptr;
+  const unsigned char* image2_2_u8 = nullptr;
+};
+
+static int pipeline_body(demon_net* n, const PipelineInput& in, int iterations, float* depth0, float* rotation,
                          float* translation, float* flow2, float* depth2, float* normal2, cudaStream_t s) {
   int rc;
-  if ((rc = import_image_pair(n, image_pair, 0, s))) return rc;
-  if (image2_2) {
-    if ((rc = import_image2_2(n, image2_2, 0, s))) return rc;
+  const long P = 192L * 256;
+  if (in.images_u8) {
+    // img8 straight from the bytes; image 2's planes go to c1y (free until conv1y runs) for the median pair
+    float* planes2 = in.image2_2_u8 ? nullptr : n->c1y->p;
+    long blocks = ((long)n->B * P + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    u8_import_kernel<<<(int)blocks, 256, 0, s>>>(in.images_u8, n->img8->p, planes2, n->B, (int)P);
+    DEMON_LAUNCH_CHECK();
+    if (in.image2_2_u8) {
+      long b2 = ((long)n->B * 48 * 64 + 255) / 256;
+      u8_planes_kernel<<<(int)b2, 256, 0, s>>>(in.image2_2_u8, n->i22->p, n->B, 48 * 64);
+      DEMON_LAUNCH_CHECK();
+    } else if ((rc = median_image2_2(n, planes2, 3 * P, s))) {
+      return rc;
+    }
   } else {
-    if ((rc = median_image2_2(n, image_pair, s))) return rc;
+    if ((rc = import_image_pair(n, in.image_pair, 0, s))) return rc;
+    if (in.image2_2) {
+      if ((rc = import_image2_2(n, in.image2_2, 0, s))) return rc;
+    } else {
+      if ((rc = median_image2_2(n, in.image_pair + 3 * P, 6 * P, s))) return rc;
+    }
   }
   if ((rc = run_flow_block(n, "netFlow1", false, s))) return rc;
   if ((rc = run_dm_block(n, "netDM1", false, s))) return rc;
@@ -941,14 +1005,33 @@ static int pipeline_body(demon_net* n, const float* image_pair, const float* ima
     if ((rc = run_dm_block(n, "netDM2", true, s, false))) return rc;
   }
   if ((rc = export_predictions(n, nullptr, flow2, depth2, normal2, rotation, translation, 0, s))) return rc;
-  const long P = 192L * 256;
-  return run_refine_block(n, image_pair, 6 * P, 1, P, n->dn2->p, 4L * 48 * 64, 4, 48, 64, depth0, s);
+  // image1 for the refinement block is read back from img8 (NHWC8: the first three channels), whatever the input kind
+  return run_refine_block(n, n->img8->p, 8 * P, 8, 1, n->dn2->p, 4L * 48 * 64, 4, 48, 64, depth0, s);
 }
+
+static int pipeline_forward_impl(demon_net* n, const PipelineInput& in, int iterations, float* depth0, float* rotation, float* translation,
+                                 float* flow2, float* depth2, float* normal2, void* stream);
 
 int demon_pipeline_forward(demon_net* n, const float* image_pair, const float* image2_2, int iterations, float* depth0, float* rotation,
                            float* translation, float* flow2, float* depth2, float* normal2, void* stream) {
   REQUIRE_READY(n);
   DEMON_REQUIRE(image_pair, "pipeline: null image_pair");
+  PipelineInput in;
+  in.image_pair = image_pair; in.image2_2 = image2_2;
+  return pipeline_forward_impl(n, in, iterations, depth0, rotation, translation, flow2, depth2, normal2, stream);
+}
+
+int demon_pipeline_forward_u8(demon_net* n, const uint8_t* images, const uint8_t* image2_2, int iterations, float* depth0, float* rotation,
+                              float* translation, float* flow2, float* depth2, float* normal2, void* stream) {
+  REQUIRE_READY(n);
+  DEMON_REQUIRE(images, "pipeline_u8: null images");
+  PipelineInput in;
+  in.images_u8 = images; in.image2_2_u8 = image2_2;
+  return pipeline_forward_impl(n, in, iterations, depth0, rotation, translation, flow2, depth2, normal2, stream);
+}
+
+static int pipeline_forward_impl(demon_net* n, const PipelineInput& in, int iterations, float* depth0, float* rotation, float* translation,
+                                 float* flow2, float* depth2, float* normal2, void* stream) {
   DEMON_REQUIRE(iterations >= 0 && iterations <= 7, "pipeline: iterations %d", iterations);
   DEMON_REQUIRE(n->RH == 192 && n->RW == 256, "pipeline: net was created with a %dx%d refinement block", n->RH, n->RW);
   cudaStream_t s = (cudaStream_t)stream;
@@ -959,8 +1042,8 @@ int demon_pipeline_forward(demon_net* n, const float* image_pair, const float* i
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(s, &cap);
   if (graphs_on && !n->profiling && cap == cudaStreamCaptureStatusNone) {
-    const std::vector<const void*> key = {image_pair, image2_2, depth0, rotation, translation, flow2, depth2, normal2,
-                                          reinterpret_cast<const void*>((intptr_t)iterations)};
+    const std::vector<const void*> key = {in.image_pair, in.image2_2, in.images_u8, in.image2_2_u8, depth0, rotation, translation, flow2, depth2,
+                                          normal2, reinterpret_cast<const void*>((intptr_t)iterations)};
     for (auto& g : n->graphs)
       if (g.key == key) {
         if (g.exec == nullptr) {   // second call: capture
@@ -968,7 +1051,7 @@ int demon_pipeline_forward(demon_net* n, const float* image_pair, const float* i
           const int64_t l0 = g_launch_count.load();
           if (!n->cap_stream) DEMON_CHECK_CUDA(cudaStreamCreateWithFlags(&n->cap_stream, cudaStreamNonBlocking));
           DEMON_CHECK_CUDA(cudaStreamBeginCapture(n->cap_stream, cudaStreamCaptureModeThreadLocal));
-          int rc = pipeline_body(n, image_pair, image2_2, iterations, depth0, rotation, translation, flow2, depth2, normal2, n->cap_stream);
+          int rc = pipeline_body(n, in, iterations, depth0, rotation, translation, flow2, depth2, normal2, n->cap_stream);
           cudaError_t e = cudaStreamEndCapture(n->cap_stream, &graph);
           if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
           if (e != cudaSuccess) return fail(DEMON_E_CUDA, "pipeline: stream capture failed: %s", cudaGetErrorString(e));
@@ -990,44 +1073,57 @@ int demon_pipeline_forward(demon_net* n, const float* image_pair, const float* i
     n->graphs.push_back({key, nullptr, 0});
   }
   const int64_t launches0 = g_launch_count.load();
-  int rc = pipeline_body(n, image_pair, image2_2, iterations, depth0, rotation, translation, flow2, depth2, normal2, s);
+  int rc = pipeline_body(n, in, iterations, depth0, rotation, translation, flow2, depth2, normal2, s);
   if (rc) return rc;
   n->pipeline_launches[iterations] = (int)(g_launch_count.load() - launches0);
   return DEMON_OK;
 }
 
-static int pipeline_host(demon_net* n, const float* image_pair_host, const float* image2_2_host, int iterations, float* depth0_host,
+static int pipeline_host(demon_net* n, const void* images_host, const void* image2_2_host, bool u8, int iterations, float* depth0_host,
                          float* rotation_host, float* translation_host, void* stream, bool sync);
 
 int demon_pipeline_forward_host(demon_net* n, const float* image_pair_host, const float* image2_2_host, int iterations, float* depth0_host,
                                 float* rotation_host, float* translation_host, void* stream) {
-  return pipeline_host(n, image_pair_host, image2_2_host, iterations, depth0_host, rotation_host, translation_host, stream, true);
+  return pipeline_host(n, image_pair_host, image2_2_host, false, iterations, depth0_host, rotation_host, translation_host, stream, true);
 }
 
 int demon_pipeline_forward_host_async(demon_net* n, const float* image_pair_host, const float* image2_2_host, int iterations,
                                       float* depth0_host, float* rotation_host, float* translation_host, void* stream) {
-  return pipeline_host(n, image_pair_host, image2_2_host, iterations, depth0_host, rotation_host, translation_host, stream, false);
+  return pipeline_host(n, image_pair_host, image2_2_host, false, iterations, depth0_host, rotation_host, translation_host, stream, false);
 }
 
-static int pipeline_host(demon_net* n, const float* image_pair_host, const float* image2_2_host, int iterations, float* depth0_host,
+int demon_pipeline_forward_host_u8(demon_net* n, const uint8_t* images_host, const uint8_t* image2_2_host, int iterations, float* depth0_host,
+                                   float* rotation_host, float* translation_host, void* stream) {
+  return pipeline_host(n, images_host, image2_2_host, true, iterations, depth0_host, rotation_host, translation_host, stream, true);
+}
+
+int demon_pipeline_forward_host_u8_async(demon_net* n, const uint8_t* images_host, const uint8_t* image2_2_host, int iterations,
+                                         float* depth0_host, float* rotation_host, float* translation_host, void* stream) {
+  return pipeline_host(n, images_host, image2_2_host, true, iterations, depth0_host, rotation_host, translation_host, stream, false);
+}
+
+static int pipeline_host(demon_net* n, const void* images_host, const void* image2_2_host, bool u8, int iterations, float* depth0_host,
                          float* rotation_host, float* translation_host, void* stream, bool sync) {
   REQUIRE_READY(n);
-  DEMON_REQUIRE(image_pair_host && depth0_host, "pipeline_host: null pointer");
+  DEMON_REQUIRE(images_host && depth0_host, "pipeline_host: null pointer");
   cudaStream_t s = (cudaStream_t)stream;
   // staging lives in buffers that are free at the respective moments:
-  //   image pair -> concat0 ([B,192,256,64]; only written by the refinement block, after `rin` has been built from it)
+  //   images     -> concat0 ([B,192,256,64]; only written by the refinement block, which reads image1 back from img8)
   //   image2_2   -> pd0a    (only written by netRefine/predict_depth0/conv1)
-  const size_t ip_bytes = (size_t)n->B * 6 * 192 * 256 * sizeof(float);
-  const size_t i22_bytes = (size_t)n->B * 3 * 48 * 64 * sizeof(float);
-  float* ip_keep = n->concat0->p;
-  float* i22_dev = n->pd0a->p;
-  DEMON_CHECK_CUDA(cudaMemcpyAsync(ip_keep, image_pair_host, ip_bytes, cudaMemcpyHostToDevice, s));
+  const size_t px = (size_t)n->B * 192 * 256;
+  const size_t ip_bytes = u8 ? px * 6 : px * 6 * sizeof(float);
+  const size_t i22_bytes = (size_t)n->B * 3 * 48 * 64 * (u8 ? 1 : sizeof(float));
+  void* ip_dev = n->concat0->p;
+  void* i22_dev = n->pd0a->p;
+  DEMON_CHECK_CUDA(cudaMemcpyAsync(ip_dev, images_host, ip_bytes, cudaMemcpyHostToDevice, s));
   if (image2_2_host) DEMON_CHECK_CUDA(cudaMemcpyAsync(i22_dev, image2_2_host, i22_bytes, cudaMemcpyHostToDevice, s));
   float* out_dev = n->rdepth0->p;
   float* rt_dev = n->fc1->p;                 // 6 floats per sample, fc1 is free after the last DM block
-  int rc = demon_pipeline_forward(n, ip_keep, image2_2_host ? i22_dev : nullptr, iterations, out_dev,
-                                  rotation_host ? rt_dev : nullptr, translation_host ? rt_dev + 3 * n->B : nullptr, nullptr, nullptr,
-                                  nullptr, stream);
+  PipelineInput in;
+  if (u8) { in.images_u8 = static_cast<const unsigned char*>(ip_dev); in.image2_2_u8 = image2_2_host ? static_cast<const unsigned char*>(i22_dev) : nullptr; }
+  else { in.image_pair = static_cast<const float*>(ip_dev); in.image2_2 = image2_2_host ? static_cast<const float*>(i22_dev) : nullptr; }
+  int rc = pipeline_forward_impl(n, in, iterations, out_dev, rotation_host ? rt_dev : nullptr, translation_host ? rt_dev + 3 * n->B : nullptr,
+                                 nullptr, nullptr, nullptr, stream);
   if (rc) return rc;
   DEMON_CHECK_CUDA(cudaMemcpyAsync(depth0_host, out_dev, (size_t)n->B * 192 * 256 * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (rotation_host) DEMON_CHECK_CUDA(cudaMemcpyAsync(rotation_host, rt_dev, (size_t)n->B * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));

@@ -301,6 +301,39 @@ class DemonPipeline:
             ptr("predict_flow2"), ptr("predict_depth2"), ptr("predict_normal2"), _stream()))
         return outputs
 
+    def forward_u8(self, images, image2_2=None, outputs=None):
+        """The pipeline on uint8 images (torch CUDA uint8): images [B,2,192,256,3] = image 1 and image 2 of every pair as
+        PIL gives them (HWC RGB), image2_2 [B,48,64,3] or None (median3x3_downsample twice).  /255 - 0.5 and the pair
+        concat run on the device (examples/example.py:15-42); same outputs as forward(), bit for bit."""
+        b = self.batch_size
+        if not (isinstance(images, torch.Tensor) and images.is_cuda and images.dtype == torch.uint8 and tuple(images.shape) == (b, 2, 192, 256, 3)):
+            raise ValueError("images: expected a CUDA uint8 tensor of shape %s" % ((b, 2, 192, 256, 3),))
+        if image2_2 is not None and not (isinstance(image2_2, torch.Tensor) and image2_2.is_cuda and image2_2.dtype == torch.uint8
+                                          and tuple(image2_2.shape) == (b, 48, 64, 3)):
+            raise ValueError("image2_2: expected a CUDA uint8 tensor of shape %s" % ((b, 48, 64, 3),))
+        images = images.contiguous()
+        if image2_2 is not None:
+            image2_2 = image2_2.contiguous()
+        if outputs is None:
+            outputs = self.own_outputs()
+        ptr = lambda k: outputs[k].data_ptr() if outputs.get(k) is not None else None
+        _lib.check(_lib.load().demon_pipeline_forward_u8(
+            self.net.ptr, images.data_ptr(), None if image2_2 is None else image2_2.data_ptr(), self.iterations,
+            ptr("predict_depth0"), ptr("predict_rotation"), ptr("predict_translation"),
+            ptr("predict_flow2"), ptr("predict_depth2"), ptr("predict_normal2"), _stream()))
+        return outputs
+
+    def forward_host_u8(self, images, image2_2, depth0, rotation, translation, stream=None, sync=True):
+        """End to end from HOST uint8 images [B,2,192,256,3] (numpy or pinned torch CPU uint8): H2D of the bytes, the
+        pipeline, D2H of depth0 / rotation / translation.  sync=False: asynchronous on `stream` like forward_host_async."""
+        def hp(x):
+            if x is None:
+                return None
+            return x.data_ptr() if isinstance(x, torch.Tensor) else x.ctypes.data
+        s = ctypes.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)
+        fn = _lib.load().demon_pipeline_forward_host_u8 if sync else _lib.load().demon_pipeline_forward_host_u8_async
+        _lib.check(fn(self.net.ptr, hp(images), hp(image2_2), self.iterations, hp(depth0), hp(rotation), hp(translation), s))
+
     def forward_host(self, image_pair, image2_2, depth0, rotation, translation):
         """End-to-end call on HOST buffers (pinned torch CPU tensors or numpy arrays): H2D, pipeline, D2H and a
         stream synchronise inside the C call."""

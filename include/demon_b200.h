@@ -165,6 +165,18 @@ int demon_pipeline_forward_host_async(demon_net* net, const float* image_pair_ho
                                       int iterations, float* depth0_host, float* rotation_host,
                                       float* translation_host, void* stream);
 
+/* The same pipeline on uint8 images, the form examples/example.py:15-42 starts from (PIL RGB, HWC): images [B,2,192,256,3]
+ * (image 1 then image 2 of every pair), image2_2 [B,48,64,3] (the resized second image) or NULL (then it is computed with
+ * median3x3_downsample twice, examples/evaluation.py:170-173).  `x/255 - 0.5` and the pair concat happen on the device in
+ * the kernel that feeds conv1y, with numpy's two float32 operations, so the outputs equal the fp32 entry's bit for bit;
+ * the host variants move 4x fewer input bytes. */
+int demon_pipeline_forward_u8(demon_net* net, const uint8_t* images, const uint8_t* image2_2, int iterations, float* depth0,
+                              float* rotation, float* translation, float* flow2, float* depth2, float* normal2, void* stream);
+int demon_pipeline_forward_host_u8(demon_net* net, const uint8_t* images_host, const uint8_t* image2_2_host, int iterations,
+                                   float* depth0_host, float* rotation_host, float* translation_host, void* stream);
+int demon_pipeline_forward_host_u8_async(demon_net* net, const uint8_t* images_host, const uint8_t* image2_2_host, int iterations,
+                                         float* depth0_host, float* rotation_host, float* translation_host, void* stream);
+
 /* introspection for tests and bench */
 int demon_net_batch(const demon_net* net);
 int64_t demon_net_workspace_bytes(const demon_net* net);

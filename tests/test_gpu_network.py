@@ -211,6 +211,33 @@ def test_pipeline_matches_stagewise_api_and_median_image2_2(sessions, random_pai
         assert np.array_equal(outs[k][0].numpy(), d0) and np.array_equal(outs[k][2].numpy(), r["predict_translation"])
 
 
+def test_uint8_entry_equals_fp32_entry_bit_for_bit(sessions, synthetic_weights):
+    """uint8 images in, `/255 - 0.5` + pair concat + median on the device.  On the repository's own
+    sculpture pair (examples/sculpture{1,2}.png, examples/example.py:15-42) and on random bytes the outputs must equal
+    those of the fp32 entry fed with numpy's float32 conversion, with image2_2 given (the resized image) and computed."""
+    import os
+    from demon_b200.networks_original import DemonPipeline
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sculpture_inputs.npz"))
+    rng = np.random.RandomState(5)
+    rnd = rng.randint(0, 256, (2, 192, 256, 3)).astype(np.uint8)
+    u8 = np.stack([np.stack([z["img1"], z["img2"]]).astype(np.uint8), rnd])                          # [2,2,192,256,3]
+    i22_u8 = np.stack([z["img2_2"].astype(np.uint8), rnd[1, 2::4, 2::4]])                             # [2,48,64,3]
+    f = lambda a: a.astype(np.float32) / 255 - 0.5                                                    # example.py:25-27
+    pair = np.concatenate([f(u8[:, 0]).transpose(0, 3, 1, 2), f(u8[:, 1]).transpose(0, 3, 1, 2)], axis=1)
+    i22 = f(i22_u8).transpose(0, 3, 1, 2)
+    pipe = DemonPipeline(sessions["3xtf32"], batch_size=2, iterations=3)
+    for with_i22 in (True, False):
+        ref = {k: v.clone() for k, v in pipe.forward(torch.from_numpy(pair).cuda(), torch.from_numpy(i22).cuda() if with_i22 else None).items()}
+        got = pipe.forward_u8(torch.from_numpy(u8).cuda(), torch.from_numpy(i22_u8).cuda() if with_i22 else None)
+        torch.cuda.synchronize()
+        for k in ref:
+            assert torch.equal(ref[k], got[k]), (k, with_i22)
+    # host entry: bytes in, depth out
+    d0 = np.empty((2, 1, 192, 256), np.float32); rot = np.empty((2, 3), np.float32); tr = np.empty((2, 3), np.float32)
+    pipe.forward_host_u8(u8, None, d0, rot, tr)
+    assert np.array_equal(d0, ref["predict_depth0"].cpu().numpy()) and np.array_equal(tr, ref["predict_translation"].cpu().numpy())
+
+
 def test_cuda_graph_replay_equals_eager(sessions, random_pairs):
     """demon_pipeline_forward replays a CUDA graph from the third call with the same pointer arguments on; the result
     must equal the eager first call bit for bit, also after the input buffer's CONTENT changes."""

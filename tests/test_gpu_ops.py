@@ -52,6 +52,21 @@ def test_median_with_nans_selects_the_reference_element(ops):
     assert np.array_equal(np.isnan(g), np.isnan(r)) and np.array_equal(g[~np.isnan(g)], r[~np.isnan(r)])
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 256), (1, 3, 33, 264), (3, 7, 512)])
+def test_median_vector_path_bit_exact_with_nans_and_ties(ops, shape):
+    """float, W a multiple of 8 and >= 256: the four-outputs-per-thread kernel (odd heights, NaNs, ties, signed zeros)."""
+    rng = np.random.RandomState(sum(shape))
+    A = (np.round(rng.rand(*shape) * 6) / 6 - 0.5).astype(np.float32)
+    A[rng.rand(*shape) < 0.1] = np.nan
+    A[rng.rand(*shape) < 0.05] = -0.0
+    A[rng.rand(*shape) < 0.05] = 0.0
+    g, r = ops.median3x3_downsample(A), oops.median3x3_downsample(A)
+    assert g.shape == r.shape
+    assert np.array_equal(np.isnan(g), np.isnan(r))
+    m = ~np.isnan(r)
+    assert np.array_equal(g[m].view(np.uint32), r[m].view(np.uint32))
+
+
 def test_median_twice_at_benchmark_size_matches_oracle(ops):
     rng = np.random.RandomState(1)
     img = rng.uniform(-0.5, 0.5, (8, 3, 192, 256)).astype(np.float32)
@@ -75,6 +90,27 @@ def test_warp2d_matches_oracle(ops, dtype, normalized, border_mode):
     g = ops.warp2d(img, disp, normalized=normalized, border_mode=border_mode, border_value=0.25)
     r = oops.warp2d(img, disp, normalized=normalized, border_mode=border_mode, border_value=0.25)
     assert g.shape == img.shape
+    assert np.array_equal(np.isnan(g), np.isnan(r))
+    m = ~np.isnan(r)
+    assert np.array_equal(g[m], r[m]), np.abs(g[m] - r[m]).max()
+
+
+@pytest.mark.parametrize("normalized", (False, True))
+@pytest.mark.parametrize("border_mode", ("clamp", "value"))
+@pytest.mark.parametrize("width", (128, 256, 260))
+def test_warp2d_vector_path_matches_oracle(ops, normalized, border_mode, width):
+    """float, W a multiple of 4 and >= 128: the four-pixels-per-thread kernel, edge cases included."""
+    rng = np.random.RandomState(width)
+    img = rng.uniform(-1, 1, (2, 3, 21, width)).astype(np.float32)
+    scale = 0.2 if normalized else 9.0
+    disp = rng.uniform(-scale, scale, (2, 2, 21, width)).astype(np.float32)
+    disp[0, 0, 0, 0] = -0.5 / (width if normalized else 1)      # p2 in (-1, 0): truncation toward zero
+    disp[0, 1, 0, 0] = -0.25 / (21 if normalized else 1)
+    disp[0, 0, 3, 4:8] = [np.nan, np.inf, -np.inf, 1e30]
+    disp[1, 1, 5, 8:12] = [np.nan, 3e9, -3e9, 0.0]
+    disp[1, :, 20, width - 4:] = 0.0                             # last row / last columns, integer position
+    g = ops.warp2d(img, disp, normalized=normalized, border_mode=border_mode, border_value=-0.75)
+    r = oops.warp2d(img, disp, normalized=normalized, border_mode=border_mode, border_value=-0.75)
     assert np.array_equal(np.isnan(g), np.isnan(r))
     m = ~np.isnan(r)
     assert np.array_equal(g[m], r[m]), np.abs(g[m] - r[m]).max()
