@@ -28,6 +28,10 @@ PROTOTYPES = {
     "demon_median3x3_downsample_f64": [_P, _P, c_int64, c_int, c_int, _P],
     "demon_scale_invariant_gradient_f32": [_P, _P, c_int64, c_int, c_int, _P, _P, c_int, c_float, _P],
     "demon_scale_invariant_gradient_f64": [_P, _P, c_int64, c_int, c_int, _P, _P, c_int, c_double, _P],
+    "demon_metric_workspace_bytes": [c_int, c_int64],
+    "demon_depth_error_sums_f32": [_P, _P, c_int, c_int64, c_int, c_int, _P, _P, _P, _P, _P],
+    "demon_depth_scale_factor": [_P, c_int, c_int, _P, _P],
+    "demon_flow_epe_sums_f32": [_P, _P, c_int, c_int64, _P, _P, _P],
     "demon_net_create": [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int],
     "demon_net_destroy": [_P],
     "demon_net_set_weight": [_P, c_char_p, _P, _P, c_int],
@@ -68,6 +72,7 @@ _RESTYPES = {
     "demon_net_variable_name": c_char_p,
     "demon_net_layer_name": c_char_p,
     "demon_net_workspace_bytes": c_int64,
+    "demon_metric_workspace_bytes": c_int64,
     "demon_last_error": c_char_p,
     "demon_version": c_char_p,
     "demon_launch_count": c_int64,

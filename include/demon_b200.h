@@ -96,6 +96,29 @@ int demon_scale_invariant_gradient_f64(const double* input, double* output, int6
                                        void* stream);
 
 /* ------------------------------------------------------------------------
+ * Evaluation metrics on the device (python/depthmotionnet/evaluation/metrics.py).
+ * One streaming pass per call; all pointers are device pointers, nothing synchronises.
+ * ---------------------------------------------------------------------- */
+#define DEMON_METRIC_SUMS 16
+/* bytes of scratch the two *_sums entries need for n samples of hw pixels */
+int64_t demon_metric_workspace_bytes(int n, int64_t hw);
+/* The masked per-sample sums behind compute_errors / evaluate_depth (metrics.py:240-372) for pred, gt [n, hw]:
+ *   mask        finite and > 0 in BOTH inputs (compute_valid_depth_mask, metrics.py:25-38), again after the transforms
+ *   transforms  reciprocal if inverse_pred / inverse_gt (metrics.py:339-342), gt / gt_div[n] if gt_div (the translation
+ *               norm, metrics.py:349-355), pred * pred_scale[n] if pred_scale (metrics.py:362)
+ *   sums[n][16] 0 num_valid, 1 sum|p-g|, 2 sum|1/p-1/g|, 3 sum ld, 4 sum ld^2 (ld = log p - log g), 5 sum|p-g|/g,
+ *               6 sum (p-g)^2/g, 7 sum|log10 p - log10 g|, 8 sum (p-g)^2, 9..11 count(|ld| < log t) for t = 1.25,
+ *               1.5625, 1.953125, 12 sum p*p and 13 sum p*g over finite positive p*g, 14 / 15 the same for 1/p, 1/g
+ *               (12..15 on the UNSCALED prediction: compute_depth_scale_factor, metrics.py:283-318)                    */
+int demon_depth_error_sums_f32(const float* pred, const float* gt, int n, int64_t hw, int inverse_pred, int inverse_gt,
+                               const float* gt_div, const float* pred_scale, double* sums, void* workspace, void* stream);
+/* scale[n] that minimises the squared error of scale * pred against gt, from the sums above, on the device
+ * (mode 0 'abs', 1 'log', 2 'inv'; metrics.py:283-318) */
+int demon_depth_scale_factor(const double* sums, int n, int mode, float* scale, void* stream);
+/* compute_flow_epe (metrics.py:377-387): flow1, flow2 [n,2,hw] -> sums[n][2] = {sum of the valid end point errors, count} */
+int demon_flow_epe_sums_f32(const float* flow1, const float* flow2, int n, int64_t hw, double* sums, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------
  * Network graphs (python/depthmotionnet/networks_original.py).
  * One handle = the five blocks netFlow1, netDM1, netFlow2, netDM2, netRefine for a
  * fixed batch size at 256x192 (networks_original.py:38-42), plus a refinement block that
