@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libdemon_b200.so")
-SOURCES = ["geometry_ops.cu", "metrics.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_halo.cu", "net.cu"]
+SOURCES = ["geometry_ops.cu", "metrics.cu", "training_ops.cu", "conv_simt.cu", "conv_tc.cu", "conv_tc_halo.cu", "net.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -231,3 +231,83 @@ def scale_invariant_gradient(input, deltas=(1,), weights=(1.0,), epsilon=0.001):
           ctypes.cast(d_arr, ctypes.c_void_p), ctypes.cast(w_arr, ctypes.c_void_p), len(deltas),
           cty(float(np.float32(epsilon))), _stream())
     return _ret(out, was_np)
+
+
+# ---- training-side companions ---------------------------------------------------------------
+def scale_invariant_gradient_grad(gradients, input, deltas=(1,), weights=(1.0,), epsilon=0.001):
+    """Gradient of scale_invariant_gradient with respect to its input: the ScaleInvariantGradientGrad op the reference
+    registers for it (scaleinvariantgradient.cc:224-404; `_scale_invariant_gradient_grad`,
+    lmbspecialops/python/lmbspecialops/__init__.py).  gradients [z,2,h,w], input [...,h,w] -> input's shape."""
+    deltas = [int(d) for d in deltas]
+    weights = [float(v) for v in weights]
+    if len(deltas) != len(weights):
+        raise ValueError("The size of the deltas and weights vectors must be the same")
+    if len(deltas) > 16:
+        raise ValueError("at most 16 deltas are supported")
+    x, was_np = _as_cuda(input)
+    g, _ = _as_cuda(gradients, x.dtype)
+    h, w = x.shape[-2:]
+    z = _prod(x.shape[:-2])
+    if tuple(g.shape) != (z, 2, h, w):
+        raise ValueError("Dimensions must be equal: gradients %s, expected %s" % (tuple(g.shape), (z, 2, h, w)))
+    out = torch.empty_like(x)
+    cty = ctypes.c_float if x.dtype == torch.float32 else ctypes.c_double
+    d_arr = (ctypes.c_int * max(1, len(deltas)))(*deltas)
+    w_arr = (cty * max(1, len(weights)))(*[float(np.float32(v)) for v in weights])
+    _call("demon_scale_invariant_gradient_grad" + _sfx(x), g.data_ptr(), x.data_ptr(), out.data_ptr(), z, h, w,
+          ctypes.cast(d_arr, ctypes.c_void_p), ctypes.cast(w_arr, ctypes.c_void_p), len(deltas),
+          cty(float(np.float32(epsilon))), _stream())
+    return _ret(out, was_np)
+
+
+def leaky_relu_grad(gradients, input, leak=0.1):
+    """LeakyReluLmbGrad (leakyrelu.cc:100-172): gradients where input >= leak*input, leak*gradients elsewhere."""
+    x, was_np = _as_cuda(input)
+    g, _ = _as_cuda(gradients, x.dtype)
+    if tuple(g.shape) != tuple(x.shape):
+        raise ValueError("Dimensions must be equal: gradients %s, input %s" % (tuple(g.shape), tuple(x.shape)))
+    out = torch.empty_like(x)
+    lk = (ctypes.c_float if x.dtype == torch.float32 else ctypes.c_double)(np.float32(leak))
+    _call("demon_leaky_relu_grad" + _sfx(x), g.data_ptr(), x.data_ptr(), out.data_ptr(), x.numel(), lk, _stream())
+    return _ret(out, was_np)
+
+
+def replace_nonfinite(input, value=0.0):
+    """Replaces NaN / inf by `value` (replacenonfinite.cc:26-93; used by the v2 losses, v2/losses.py:49)."""
+    x, was_np = _as_cuda(input)
+    out = torch.empty_like(x)
+    v = (ctypes.c_float if x.dtype == torch.float32 else ctypes.c_double)(np.float32(value))
+    _call("demon_replace_nonfinite" + _sfx(x), x.data_ptr(), out.data_ptr(), x.numel(), v, _stream())
+    return _ret(out, was_np)
+
+
+def replace_nonfinite_grad(gradients, input):
+    """ReplaceNonfiniteGrad (replacenonfinite.cc:97-168): zero gradient where the input was not finite."""
+    x, was_np = _as_cuda(input)
+    g, _ = _as_cuda(gradients, x.dtype)
+    if tuple(g.shape) != tuple(x.shape):
+        raise ValueError("Dimensions must be equal: gradients %s, input %s" % (tuple(g.shape), tuple(x.shape)))
+    out = torch.empty_like(x)
+    _call("demon_replace_nonfinite_grad" + _sfx(x), g.data_ptr(), x.data_ptr(), out.data_ptr(), x.numel(), _stream())
+    return _ret(out, was_np)
+
+
+class _SIGFunction(torch.autograd.Function):
+    """torch.autograd counterpart of the @ops.RegisterGradient("ScaleInvariantGradient") hook of the reference binding."""
+
+    @staticmethod
+    def forward(ctx, x, deltas, weights, epsilon):
+        ctx.save_for_backward(x)
+        ctx.attrs = (deltas, weights, epsilon)
+        return scale_invariant_gradient(x, deltas, weights, epsilon)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (x,) = ctx.saved_tensors
+        deltas, weights, epsilon = ctx.attrs
+        return scale_invariant_gradient_grad(grad_out.contiguous(), x, deltas, weights, epsilon), None, None, None
+
+
+def scale_invariant_gradient_autograd(input, deltas=(1,), weights=(1.0,), epsilon=0.001):
+    """scale_invariant_gradient on a torch CUDA tensor with the reference's analytic gradient attached."""
+    return _SIGFunction.apply(input, tuple(deltas), tuple(weights), float(epsilon))

@@ -96,6 +96,24 @@ int demon_scale_invariant_gradient_f64(const double* input, double* output, int6
                                        void* stream);
 
 /* ------------------------------------------------------------------------
+ * Training-side companions: the gradient kernels the reference registers for the ops above
+ * and the element-wise ReplaceNonfinite of its v2 losses.  Same collapsing of leading dimensions as the forward ops.
+ * ---------------------------------------------------------------------- */
+/* Replaces ScaleInvariantGradientGradOp (scaleinvariantgradient.cc:294-404): gradients [z,2,h,w], input [z,h,w] -> [z,h,w] */
+int demon_scale_invariant_gradient_grad_f32(const float* gradients, const float* input, float* output, int64_t z, int h, int w,
+                                            const int* deltas, const float* weights, int num, float epsilon, void* stream);
+int demon_scale_invariant_gradient_grad_f64(const double* gradients, const double* input, double* output, int64_t z, int h, int w,
+                                            const int* deltas, const double* weights, int num, double epsilon, void* stream);
+/* Replaces LeakyReluLmbGradOp (leakyrelu.cc:127-155) */
+int demon_leaky_relu_grad_f32(const float* gradients, const float* input, float* output, int64_t size, float leak, void* stream);
+int demon_leaky_relu_grad_f64(const double* gradients, const double* input, double* output, int64_t size, double leak, void* stream);
+/* Replaces ReplaceNonfiniteOp / ReplaceNonfiniteGradOp (replacenonfinite.cc:49-80,115-150) */
+int demon_replace_nonfinite_f32(const float* input, float* output, int64_t size, float value, void* stream);
+int demon_replace_nonfinite_f64(const double* input, double* output, int64_t size, double value, void* stream);
+int demon_replace_nonfinite_grad_f32(const float* gradients, const float* input, float* output, int64_t size, void* stream);
+int demon_replace_nonfinite_grad_f64(const double* gradients, const double* input, double* output, int64_t size, void* stream);
+
+/* ------------------------------------------------------------------------
  * Evaluation metrics on the device (python/depthmotionnet/evaluation/metrics.py).
  * One streaming pass per call; all pointers are device pointers, nothing synchronises.
  * ---------------------------------------------------------------------- */

@@ -1,5 +1,5 @@
 """ORACLE (test infrastructure) -- the reference's OWN CPU op kernels, compiled here from
-/root/reference/lmbspecialops/src/{warp2d,median3x3downsample,scaleinvariantgradient,leakyrelu,depthtoflow}.cc
+/root/reference/lmbspecialops/src/{warp2d,median3x3downsample,scaleinvariantgradient,leakyrelu,depthtoflow,replacenonfinite}.cc
 (unmodified, read where they lie) against the stub TensorFlow / Eigen headers in oracle/ref_stub/, as
 oracle/_ref/libref_ops.so (git-ignored, travels to the GPU box with the snapshot).
 
@@ -17,7 +17,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_ref", "libref_ops.so")
 REF_SRC = "/root/reference/lmbspecialops/src"
-_SOURCES = ["warp2d.cc", "median3x3downsample.cc", "scaleinvariantgradient.cc", "leakyrelu.cc", "depthtoflow.cc"]
+_SOURCES = ["warp2d.cc", "median3x3downsample.cc", "scaleinvariantgradient.cc", "leakyrelu.cc", "depthtoflow.cc", "replacenonfinite.cc"]
 
 
 def build(force=False):
@@ -28,7 +28,7 @@ def build(force=False):
     deps = [os.path.join(REF_SRC, s) for s in _SOURCES] + [os.path.join(_HERE, f) for f in (
         "ref_harness.cc", "ref_stub/tf_stub.h", "ref_stub/eigen_stub.h", "Makefile")]
     if force or not os.path.isfile(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(d) for d in deps):
-        subprocess.check_call(["make", "-C", _HERE, "-s", "ref"] + (["-B"] if force else []))
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "ref"])   # this function decided it is stale (make does not see Makefile edits)
     return _LIB_PATH
 
 
@@ -124,3 +124,13 @@ def depth_to_flow(depth, intrinsics, rotation, translation, rotation_format="ang
     """DepthToFlowOp::Compute, depthtoflow.cc:211-313 (Eigen's rotation conversions come from oracle/ref_stub/eigen_stub.h)."""
     return run("DepthToFlow", [depth, intrinsics, rotation, translation],
                "rotation_format:s=%s;inverse_depth:b=%s;normalize_flow:b=%s" % (rotation_format, _b(inverse_depth), _b(normalize_flow)))
+
+
+def replace_nonfinite(input, value=0.0):
+    """ReplaceNonfiniteOp::Compute, replacenonfinite.cc:60-80."""
+    return run("ReplaceNonfinite", [input], "value:f=%r" % float(value))
+
+
+def replace_nonfinite_grad(gradients, input):
+    """ReplaceNonfiniteGradOp::Compute, replacenonfinite.cc:123-150."""
+    return run("ReplaceNonfiniteGrad", [gradients, input])
