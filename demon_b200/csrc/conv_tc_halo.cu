@@ -126,8 +126,14 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint
 // through a vector register and an R2UR per step).  Fast path: one try_wait.  Slow path: spin with a cycle budget; the
 // cycles spent there go to `acc` (the wait counters of the debug timing cost nothing on the fast path).  On timeout the
 // error flag is raised and the kernel runs to completion with garbage; the host turns the flag into DEMON_E_STATE.
-__device__ __forceinline__ void wait_t(uint32_t bar, uint32_t parity, int* err, long long& acc, bool /*timed*/) {
-  if (mbar_try(bar, parity)) return;
+__device__ __forceinline__ void wait_t(uint32_t bar, uint32_t parity, int* err, long long& acc, bool timed) {
+  // (a try_wait on a pending phase may suspend the thread in hardware and still return true: with `timed` the whole
+  // call is bracketed, otherwise only the spin path is)
+  const long long t_in = timed ? clock64() : 0;
+  if (mbar_try(bar, parity)) {
+    if (timed) acc += clock64() - t_in;
+    return;
+  }
   const long long t0 = clock64();
   for (;;) {
     if (mbar_try(bar, parity)) break;
@@ -136,7 +142,7 @@ __device__ __forceinline__ void wait_t(uint32_t bar, uint32_t parity, int* err, 
       break;
     }
   }
-  acc += clock64() - t0;
+  acc += clock64() - (timed ? t_in : t0);
 }
 
 // x / d for small d by one multiply (mul = 2^32 / d + 1, exact while x * d < 2^32; d == 1 -> mul = 0): the tile decode
@@ -199,18 +205,24 @@ __device__ __forceinline__ void issue_block(const MmaCtx& c, uint32_t d, uint32_
   }
 }
 
-// one step with the ring slot as a compile-time constant.  `rdy`: the poll of this step's barrier (issued during the
-// previous step) already saw the phase complete; on return it holds the poll of the next step's barrier.
-template <int MODE, int SLOT>
-__device__ __forceinline__ void mma_step(const MmaCtx& c, uint32_t d_base, uint32_t par, uint32_t npar, uint32_t cm, uint32_t fm,
-                                         bool& rdy, long long& w_full, bool timed) {
-  if (!rdy) wait_t(c.full0 + 8 * SLOT, par, c.err, w_full, timed);
+// One step with the ring slot as a compile-time constant (the main loop is unrolled by kRing, so the slot is the
+// position in the unrolled body and every operand address is a loop-invariant base plus an immediate).
+//   - wait for full[SLOT] unless the early poll issued during the previous step already saw the phase complete
+//   - poll full[SLOT + 1] (mbarrier.test_wait: never suspends the thread) BEFORE issuing, so that its latency overlaps the
+//     UTCHMMA issue
+//   - the step's MMAs: single-class layers (MULTI == false) one block, fresh only at the first step of a tile;
+//     transposed convolutions walk the class mask of the step
+//   - ONE commit: frees the TMEM columns (stagers) and the weight slot (W producer)
+template <int MODE, int SLOT, bool MULTI>
+__device__ __forceinline__ bool mma_step(const MmaCtx& c, uint32_t d_base, uint32_t par, uint32_t npar, bool rdy, bool fresh, uint32_t cm,
+                                         uint32_t fm, long long& w_full) {
+  if (!rdy) wait_t(c.full0 + 8 * SLOT, par, c.err, w_full, false);   // (the MMA thread's waits are never bracketed: no clock reads on its fast path)
   tc_fence_after();
-  rdy = mbar_try(c.full0 + 8 * ((SLOT + 1) & (kRing - 1)), npar);   // poll the NEXT step's barrier before issuing
+  const bool next_rdy = mbar_test(c.full0 + 8 * ((SLOT + 1) & (kRing - 1)), npar);
   const uint32_t a_hi = c.t_ring + (uint32_t)(SLOT * 64);
   uint32_t wb = c.w_ring + (uint32_t)SLOT * c.w_stage_bytes;
-  if (cm == 1u) {
-    issue_block<MODE>(c, d_base, a_hi, wb, (fm & 1u) != 0);
+  if (!MULTI) {
+    issue_block<MODE>(c, d_base, a_hi, wb, fresh);
   } else {
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -219,7 +231,60 @@ __device__ __forceinline__ void mma_step(const MmaCtx& c, uint32_t d_base, uint3
         wb += c.cls_bytes;
       }
   }
-  umma_commit(c.free0 + 8 * SLOT);   // ONE commit frees the TMEM columns (stagers) and the weight slot (W producer)
+  umma_commit(c.free0 + 8 * SLOT);
+  return next_rdy;
+}
+
+// The MMA thread's whole main loop.  State per step is kept minimal: l (step inside the tile), the early-poll flag, the
+// ring parity; everything else is loop invariant.  The tile boundary is handled inline after the step that ends a tile.
+template <int MODE, bool MULTI>
+__device__ __forceinline__ void mma_main_loop(const HaloParams& p, const MmaCtx& c, uint32_t tmem_base, int acc_cols, uint32_t cfull0,
+                                              uint32_t cempty0, long long& w_cempty, long long& w_full) {
+  const int steps_per_tile = p.k_chunks * p.nsteps;
+  const int nsteps = p.nsteps;
+  const int nbuf = p.nbuf;
+  uint64_t cmasks = 0, fmasks = 0;   // class / fresh masks of the steps of a chunk, four bits per step (MULTI only)
+  if (MULTI)
+    for (int t = 0; t < nsteps; ++t) { cmasks |= (uint64_t)p.st_cmask[t] << (4 * t); fmasks |= (uint64_t)p.st_fmask[t] << (4 * t); }
+  int tile = blockIdx.x;
+  if (tile >= p.total_tiles) return;
+  int it = 0, l = 0, t = 0;
+  uint32_t par = 0;
+  wait_t(cempty0, 1u, c.err, w_cempty, false);          // accumulator buffer 0, first use
+  uint32_t d_base = tmem_base;
+  uint32_t cfull_bar = cfull0;
+  bool rdy = mbar_test(c.full0, 0);
+
+#define DEMON_MMA_STEP(SLOT)                                                                                              \
+  {                                                                                                                       \
+    uint32_t cm = 1u, fm = 0u;                                                                                            \
+    if (MULTI) {                                                                                                          \
+      cm = (uint32_t)(cmasks >> (4 * t)) & 15u;                                                                           \
+      fm = (l < nsteps) ? ((uint32_t)(fmasks >> (4 * t)) & 15u) : 0u;                                                     \
+      if (++t == nsteps) t = 0;                                                                                           \
+    }                                                                                                                     \
+    rdy = mma_step<MODE, SLOT, MULTI>(c, d_base, par, (SLOT == kRing - 1) ? (par ^ 1u) : par, rdy, l == 0, cm, fm, w_full); \
+    if (++l == steps_per_tile) {                                                                                          \
+      umma_commit(cfull_bar);   /* the tile's accumulators are complete once everything issued so far has retired */      \
+      tile += gridDim.x;                                                                                                  \
+      if (tile >= p.total_tiles) return;                                                                                  \
+      ++it;                                                                                                               \
+      l = 0;                                                                                                              \
+      const int a = (nbuf == 2) ? (it & 1) : 0;                                                                           \
+      const uint32_t cphase = (nbuf == 2) ? ((it >> 1) & 1) : (it & 1);                                                   \
+      wait_t(cempty0 + 8 * a, cphase ^ 1u, c.err, w_cempty, false);                                                       \
+      d_base = tmem_base + (uint32_t)(a * acc_cols);                                                                      \
+      cfull_bar = cfull0 + 8 * a;                                                                                         \
+    }                                                                                                                     \
+  }
+  for (;;) {
+    DEMON_MMA_STEP(0)
+    DEMON_MMA_STEP(1)
+    DEMON_MMA_STEP(2)
+    DEMON_MMA_STEP(3)
+    par ^= 1u;
+  }
+#undef DEMON_MMA_STEP
 }
 
 template <bool PER_TAP, bool CIN8, int MODE>
@@ -336,35 +401,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
       c.n_tile = (uint32_t)p.n_tile; c.acc_w = (uint32_t)p.acc_w;
       c.idesc = umma_idesc_tf32(p.n_tile); c.idesc2 = umma_idesc_tf32(2 * p.n_tile);
       c.err = p.err;
-      // class / fresh masks of the steps of a chunk, four bits per step
-      uint64_t cmasks = 0, fmasks = 0;
-      for (int t = 0; t < p.nsteps; ++t) { cmasks |= (uint64_t)p.st_cmask[t] << (4 * t); fmasks |= (uint64_t)p.st_fmask[t] << (4 * t); }
-      const int nsteps = p.nsteps;
       long long w_cempty = 0, w_full = 0;
       const long long t_begin = clock64();
-      int it = 0;
-      uint32_t g = 0;   // global step counter of this CTA: slot = g & 3, parity = (g >> 2) & 1
-      bool rdy = mbar_try(full0, 0);
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        const int a = (p.nbuf == 2) ? (it & 1) : 0;
-        const uint32_t cphase = (p.nbuf == 2) ? ((it >> 1) & 1) : (it & 1);
-        wait_t(cempty0 + 8 * a, cphase ^ 1, p.err, w_cempty, timed);
-        const uint32_t d_base = tmem_base + (uint32_t)(a * acc_cols);
-        int t = 0;
-        for (int l = 0; l < steps_per_tile; ++l, ++g) {
-          const uint32_t cm = (uint32_t)(cmasks >> (4 * t)) & 15u;
-          const uint32_t fm = (l < nsteps) ? ((uint32_t)(fmasks >> (4 * t)) & 15u) : 0u;
-          const uint32_t par = (g >> 2) & 1u, npar = ((g + 1) >> 2) & 1u;
-          switch (g & 3u) {
-            case 0: mma_step<MODE, 0>(c, d_base, par, npar, cm, fm, rdy, w_full, timed); break;
-            case 1: mma_step<MODE, 1>(c, d_base, par, npar, cm, fm, rdy, w_full, timed); break;
-            case 2: mma_step<MODE, 2>(c, d_base, par, npar, cm, fm, rdy, w_full, timed); break;
-            default: mma_step<MODE, 3>(c, d_base, par, npar, cm, fm, rdy, w_full, timed); break;
-          }
-          if (++t == nsteps) t = 0;
-        }
-        umma_commit(cfull0 + 8 * a);   // the tile's accumulators are complete once everything issued so far has retired
-      }
+      if (p.nclass == 1) mma_main_loop<MODE, false>(p, c, tmem_base, acc_cols, cfull0, cempty0, w_cempty, w_full);
+      else mma_main_loop<MODE, true>(p, c, tmem_base, acc_cols, cfull0, cempty0, w_cempty, w_full);
       if (timed) {
         long long* tm = p.timing + blockIdx.x * 16;
         tm[2] = w_cempty; tm[3] = w_full; tm[9] = clock64() - t_begin;
@@ -381,13 +421,15 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
     const int m = q * 32 + lane;
     const int g8 = m >> 3, r = m & 7;
     const int ngroups = p.ngroups;
-    int sa = 0;
-    uint32_t pa = 0;
     long long w_safull = 0, w_free = 0;
     const long long t_begin = clock64();
-    int slot = 0;       // = step % kRing, kept incrementally
-    uint32_t use = 0;   // parity of step / kRing
-    int turn = 0;       // = step % ngroups
+    // The group visits only its OWN steps: global step gs = grp, grp + G, grp + 2G, ...; t_own is that step's index
+    // inside the current chunk.  Ring slot and parity follow from gs; in per-tap mode so does the A stage (one per step).
+    uint32_t gs = (uint32_t)grp;
+    int t_own = grp;
+    int sa = PER_TAP ? (grp % p.sa) : 0;          // halo mode: stage of the current chunk; per-tap: stage of step gs
+    uint32_t pa = PER_TAP ? (uint32_t)((grp / p.sa) & 1) : 0u;
+    const int nsteps = p.nsteps;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       for (int kc = 0; kc < p.k_chunks; ++kc) {
         uint32_t abase = 0;
@@ -396,21 +438,18 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
           __syncwarp();
           abase = smem_u32(smem + (size_t)sa * a_stage_bytes);
         }
-        for (int t = 0; t < p.nsteps; ++t) {
-          const int slot_cur = slot;
-          const uint32_t use_cur = use;
-          if (++slot == kRing) { slot = 0; use ^= 1; }
+        for (; t_own < nsteps; t_own += ngroups, gs += (uint32_t)ngroups) {
+          const int t = t_own;
+          const int slot_cur = (int)(gs & (kRing - 1));
+          const uint32_t use_cur = (gs >> 2) & 1u;
           const int sa_cur = sa;
-          const uint32_t pa_cur = pa;
-          if (PER_TAP) { if (++sa == p.sa) { sa = 0; pa ^= 1; } }   // one A stage per step
-          const bool mine = (turn == grp);
-          if (++turn == ngroups) turn = 0;
-          if (!mine) continue;
           uint32_t row;
           if (PER_TAP) {
-            wait_t(afull0 + 8 * sa_cur, pa_cur, p.err, w_safull, timed);
+            wait_t(afull0 + 8 * sa_cur, pa, p.err, w_safull, timed);
             __syncwarp();
             row = smem_u32(smem + (size_t)sa_cur * a_stage_bytes) + (uint32_t)(g8 * 1024 + r * 128);
+            sa += ngroups;                                  // the A stage of this group's next step
+            while (sa >= p.sa) { sa -= p.sa; pa ^= 1u; }
           } else if (!CIN8) {
             const HaloPlane& pl = p.planes[p.st_plane[t]];
             row = abase + (uint32_t)(pl.smem_off + p.st_aoff[t] + g8 * pl.cols * 128 + r * 128);
@@ -451,7 +490,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
           tmem_st_x32(taddr, hi);
           if (MODE != 0) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) lo[c] = __float_as_uint(tf32_lo(__uint_as_float(hi[c])));
+            for (int c = 0; c < 32; c += 2) tf32_lo2(hi[c], hi[c + 1], lo[c], lo[c + 1]);
             tmem_st_x32(taddr + 32, lo);
           }
           tmem_st_wait();
@@ -462,6 +501,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
             if (PER_TAP) mbar_arrive(aempty0 + 8 * sa_cur);   // the shift's tile has been consumed: stage back to the producer
           }
         }
+        t_own -= nsteps;   // index of the next own step inside the NEXT chunk
         if (!PER_TAP) {
           __syncwarp();
           if (lane == 0) mbar_arrive(aempty0 + 8 * sa);   // this warp is done reading the halo stage

@@ -175,6 +175,14 @@ __device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// two at a time with the packed fp32 pipe (sub.f32x2: one instruction for two subtractions; the result is exact either
+// way, x - trunc(x) only has bits below the truncation point)
+__device__ __forceinline__ void tf32_lo2(uint32_t x0, uint32_t x1, uint32_t& l0, uint32_t& l1) {
+  const uint32_t h0 = x0 & 0xFFFFE000u, h1 = x1 & 0xFFFFE000u;
+  asm("{\n.reg .b64 a, b, d;\nmov.b64 a, {%2, %3};\nmov.b64 b, {%4, %5};\nsub.f32x2 d, a, b;\nmov.b64 {%0, %1}, d;\n}"
+      : "=r"(l0), "=r"(l1)
+      : "r"(x0), "r"(x1), "r"(h0), "r"(h1));
+}
 
 // lo image = A - trunc_tf32(A) for `nvec` 16-byte vectors, 128 cooperating threads (t = 0..127); elementwise on the
 // swizzled bytes, so layout agnostic.  Four independent loads in flight per thread.
