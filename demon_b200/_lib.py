@@ -68,6 +68,7 @@ PROTOTYPES = {
     "demon_check_errors": [],
     "demon_debug_describe_layers": [_P, _P, c_int],
     "demon_debug_describe_conv": [c_int] * 13 + [_P, c_int],
+    "demon_debug_last_conv_ms": [],
     "demon_debug_tc_timing": [c_int, _P, c_int],
     "demon_conv2d_nhwc": [_P, _P] + [c_int] * 9 + [_P, _P, c_int, c_int, _P],
     "demon_deconv4x4s2_nhwc": [_P, _P] + [c_int] * 5 + [_P, _P, c_int, c_int, _P],
@@ -84,6 +85,7 @@ _RESTYPES = {
     "demon_last_error": c_char_p,
     "demon_version": c_char_p,
     "demon_launch_count": c_int64,
+    "demon_debug_last_conv_ms": c_double,
 }
 
 _lib = None

@@ -54,9 +54,33 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed")
     # the driver API (cuTensorMapEncodeTiled) is resolved at run time through cudaGetDriverEntryPoint
-    subprocess.check_call([nvcc, "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    tmp = LIB_PATH + ".tmp"   # link beside the target and rename: a snapshot never sees a half-written library
+    subprocess.check_call([nvcc, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
 
+def build_variant(name, extra_flags):
+    """Diagnostic builds (e.g. -DDEMON_TC_TIMING_FULL) next to the product library: lib/variants/<name>/libdemon_b200.so,
+    selected at run time with DEMON_B200_LIB."""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    out_dir = os.path.join(LIB_DIR, "variants", name)
+    os.makedirs(out_dir, exist_ok=True)
+    procs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(out_dir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        procs.append(subprocess.Popen([nvcc] + NVCC_FLAGS + list(extra_flags) + ["-c", os.path.join(CSRC, src), "-o", obj]))
+    if any(p.wait() != 0 for p in procs):
+        raise RuntimeError("nvcc failed")
+    path = os.path.join(out_dir, "libdemon_b200.so")
+    subprocess.check_call([nvcc, "-shared", "-o", path] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    return path
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

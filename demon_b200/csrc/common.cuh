@@ -43,6 +43,32 @@ extern std::atomic<int64_t> g_launch_count;
     if (!(cond)) return ::demon::fail(DEMON_E_INVALID, __VA_ARGS__); \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------
+// The pipeline is a chain of ~270 short kernels on one stream.  A kernel launched through launch_pdl() may become
+// resident while its predecessor is still draining: its prologue (barrier init, TMEM allocation, tensor-map prefetch,
+// parameter loads, the first weight blocks) overlaps the predecessor's tail, and the launch latency disappears from the
+// chain.  Contract: such a kernel calls pdl_wait() before it reads anything an earlier kernel wrote and before its first
+// global store (buffers are reused along the chain), and every kernel calls pdl_launch_dependents() early so that its
+// successor may start.  DEMON_PDL=0 falls back to plain stream order (for A/B measurements).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -19,6 +19,8 @@ constexpr int BK = 16;
 template <int BM, int BN>
 __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvProblem p) {
   static_assert(BM * BN == 4096, "256 threads x 16 outputs");
+  pdl_launch_dependents();   // (common.cuh: the next kernel may start its prologue)
+  pdl_wait();                // inputs come from the previous kernel; the output buffer may still be in use by it
   constexpr int ROWS_PER_THREAD_LD = BM / 64;   // A-tile float4 loads per thread
   constexpr int TXN = BN / 4;                   // thread columns
   __shared__ __align__(16) float As[BK][BM + 4];
@@ -176,6 +178,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvProblem p) {
 constexpr int kSmallCoutGroups = 4;
 template <int COUT, int LPP, int NT>   // NT: compile-time tap count (9 = 3x3) or 0 = run-time loop
 __global__ void __launch_bounds__(128) conv_small_cout_kernel(const ConvProblem p) {
+  pdl_launch_dependents();
   __shared__ __align__(16) float ws[kMaxTaps * 32 * COUT];
   const int nw = p.ntaps * p.Cin;
   for (int i = threadIdx.x; i < nw * COUT; i += 128) {
@@ -183,6 +186,7 @@ __global__ void __launch_bounds__(128) conv_small_cout_kernel(const ConvProblem 
     ws[i] = (co < p.Cout) ? __ldg(p.w + (size_t)k * p.Cout_pad + co) : 0.f;
   }
   __syncthreads();
+  pdl_wait();   // the weights above are constants; activations come from the previous kernel
   constexpr int PPB = 128 / LPP;
   const int pix = threadIdx.x / LPP, chunk = threadIdx.x % LPP;
   const int oy = blockIdx.y, n = blockIdx.z;
@@ -246,6 +250,7 @@ __global__ void __launch_bounds__(128) conv_small_cout_kernel(const ConvProblem 
 // shuffles and the 6-of-8 active lanes cost more than the uncoalesced loads), slower for 16 -> 1 at 192x256 (0.27 vs 0.16 ms)
 template <int COUT>
 __global__ void __launch_bounds__(128) conv_small_cout_pixel_kernel(const ConvProblem p) {
+  pdl_launch_dependents();
   __shared__ float ws[kMaxTaps * 32 * COUT];
   const int nw = p.ntaps * p.Cin;
   for (int i = threadIdx.x; i < nw * COUT; i += 128) {
@@ -253,6 +258,7 @@ __global__ void __launch_bounds__(128) conv_small_cout_pixel_kernel(const ConvPr
     ws[i] = (co < p.Cout) ? __ldg(p.w + (size_t)k * p.Cout_pad + co) : 0.f;
   }
   __syncthreads();
+  pdl_wait();   // the weights above are constants; activations come from the previous kernel
   const int ox = blockIdx.x * 128 + threadIdx.x, oy = blockIdx.y, n = blockIdx.z;
   if (ox >= p.Wo) return;
   float acc[COUT];
@@ -286,6 +292,8 @@ __global__ void __launch_bounds__(128) conv_small_cout_pixel_kernel(const ConvPr
 
 // out[m][c] = act(bias[c] + sum_z partial[z][m][c]); only used for 1x1 problems on 1x1 images (dense layers)
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const ConvProblem p, int ksplit, int M) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= M * p.Cout) return;
   const int m = i / p.Cout, c = i - m * p.Cout;
@@ -299,6 +307,10 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const ConvProblem p,
 
 }  // namespace
 
+// every launch may start while its predecessor drains (common.cuh: launch_pdl); a failed launch is picked up by
+// DEMON_LAUNCH_CHECK through cudaPeekAtLastError
+#define SIMT_LAUNCH(kernel, grid, block, ...) (void)launch_pdl(kernel, dim3(grid), dim3(block), 0, stream, __VA_ARGS__)
+
 int conv_simt_launch(const ConvProblem& p, cudaStream_t stream) {
   DEMON_REQUIRE(p.in && p.out && p.w && p.bias, "conv: null pointer");
   DEMON_REQUIRE((p.Cin & 3) == 0 && (p.in_pitch & 3) == 0 && (p.Cout_pad & 3) == 0, "conv: Cin (%d), in_pitch (%d), Cout_pad (%d) must be multiples of 4", p.Cin, p.in_pitch, p.Cout_pad);
@@ -311,18 +323,18 @@ int conv_simt_launch(const ConvProblem& p, cudaStream_t stream) {
     static const int pixel_mode = []() { const char* e = getenv("DEMON_SMALL_COUT_PIXEL"); return e ? atoi(e) : 2; }();   // 0: lane sharing everywhere, 1: pixel kernel everywhere, 2 (default, measured): lane sharing for Cout == 1 only
     if (pixel_mode == 1 || (pixel_mode == 2 && p.Cout > 1)) {
       dim3 g1(ceil_div(p.Wo, 128), p.Ho, p.B);
-      if (p.Cout == 1) conv_small_cout_pixel_kernel<1><<<g1, 128, 0, stream>>>(p);
-      else conv_small_cout_pixel_kernel<4><<<g1, 128, 0, stream>>>(p);
+      if (p.Cout == 1) SIMT_LAUNCH((conv_small_cout_pixel_kernel<1>), g1, 128, p);
+      else SIMT_LAUNCH((conv_small_cout_pixel_kernel<4>), g1, 128, p);
       DEMON_LAUNCH_CHECK();
       return DEMON_OK;
     }
     const int lpp = (p.Cin <= 16) ? 4 : 8;   // lanes per output pixel, one float4 of channels each
     dim3 grid(ceil_div(p.Wo, (128 / lpp) * kSmallCoutGroups), p.Ho, p.B);
     const bool nine = p.ntaps == 9;
-    if (p.Cout == 1 && lpp == 4) { if (nine) conv_small_cout_kernel<1, 4, 9><<<grid, 128, 0, stream>>>(p); else conv_small_cout_kernel<1, 4, 0><<<grid, 128, 0, stream>>>(p); }
-    else if (p.Cout == 1) { if (nine) conv_small_cout_kernel<1, 8, 9><<<grid, 128, 0, stream>>>(p); else conv_small_cout_kernel<1, 8, 0><<<grid, 128, 0, stream>>>(p); }
-    else if (lpp == 4) { if (nine) conv_small_cout_kernel<4, 4, 9><<<grid, 128, 0, stream>>>(p); else conv_small_cout_kernel<4, 4, 0><<<grid, 128, 0, stream>>>(p); }
-    else { if (nine) conv_small_cout_kernel<4, 8, 9><<<grid, 128, 0, stream>>>(p); else conv_small_cout_kernel<4, 8, 0><<<grid, 128, 0, stream>>>(p); }
+    if (p.Cout == 1 && lpp == 4) { if (nine) SIMT_LAUNCH((conv_small_cout_kernel<1, 4, 9>), grid, 128, p); else SIMT_LAUNCH((conv_small_cout_kernel<1, 4, 0>), grid, 128, p); }
+    else if (p.Cout == 1) { if (nine) SIMT_LAUNCH((conv_small_cout_kernel<1, 8, 9>), grid, 128, p); else SIMT_LAUNCH((conv_small_cout_kernel<1, 8, 0>), grid, 128, p); }
+    else if (lpp == 4) { if (nine) SIMT_LAUNCH((conv_small_cout_kernel<4, 4, 9>), grid, 128, p); else SIMT_LAUNCH((conv_small_cout_kernel<4, 4, 0>), grid, 128, p); }
+    else { if (nine) SIMT_LAUNCH((conv_small_cout_kernel<4, 8, 9>), grid, 128, p); else SIMT_LAUNCH((conv_small_cout_kernel<4, 8, 0>), grid, 128, p); }
     DEMON_LAUNCH_CHECK();
     return DEMON_OK;
   }
@@ -333,20 +345,20 @@ int conv_simt_launch(const ConvProblem& p, cudaStream_t stream) {
   // tile choice: widest N tile that the layer fills
   if (p.Cout > 32) {
     dim3 grid(ceil_div((int)M, 64), ceil_div(p.Cout, 64), ks);
-    conv_simt_kernel<64, 64><<<grid, 256, 0, stream>>>(q);
+    SIMT_LAUNCH((conv_simt_kernel<64, 64>), grid, 256, q);
   } else if (p.Cout > 16) {
     dim3 grid(ceil_div((int)M, 128), ceil_div(p.Cout, 32), ks);
-    conv_simt_kernel<128, 32><<<grid, 256, 0, stream>>>(q);
+    SIMT_LAUNCH((conv_simt_kernel<128, 32>), grid, 256, q);
   } else if (p.Cout > 8) {
     dim3 grid(ceil_div((int)M, 256), ceil_div(p.Cout, 16), ks);
-    conv_simt_kernel<256, 16><<<grid, 256, 0, stream>>>(q);
+    SIMT_LAUNCH((conv_simt_kernel<256, 16>), grid, 256, q);
   } else {
     dim3 grid(ceil_div((int)M, 512), ceil_div(p.Cout, 8), ks);
-    conv_simt_kernel<512, 8><<<grid, 256, 0, stream>>>(q);
+    SIMT_LAUNCH((conv_simt_kernel<512, 8>), grid, 256, q);
   }
   DEMON_LAUNCH_CHECK();
   if (ks > 1) {
-    splitk_reduce_kernel<<<ceil_div((int)M * p.Cout, 256), 256, 0, stream>>>(q, ks, (int)M);
+    SIMT_LAUNCH(splitk_reduce_kernel, ceil_div((int)M * p.Cout, 256), 256, q, ks, (int)M);
     DEMON_LAUNCH_CHECK();
   }
   return DEMON_OK;

@@ -216,7 +216,11 @@ __device__ __forceinline__ void issue_block(const MmaCtx& c, uint32_t d, uint32_
 template <int MODE, int SLOT, bool MULTI>
 __device__ __forceinline__ bool mma_step(const MmaCtx& c, uint32_t d_base, uint32_t par, uint32_t npar, bool rdy, bool fresh, uint32_t cm,
                                          uint32_t fm, long long& w_full) {
+#ifdef DEMON_TC_TIMING_FULL
+  if (!rdy) wait_t(c.full0 + 8 * SLOT, par, c.err, w_full, true);    // diagnostic build: every wait bracketed by clock reads
+#else
   if (!rdy) wait_t(c.full0 + 8 * SLOT, par, c.err, w_full, false);   // (the MMA thread's waits are never bracketed: no clock reads on its fast path)
+#endif
   tc_fence_after();
   const bool next_rdy = mbar_test(c.full0 + 8 * ((SLOT + 1) & (kRing - 1)), npar);
   const uint32_t a_hi = c.t_ring + (uint32_t)(SLOT * 64);
@@ -331,7 +335,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
   const int acc_cols = p.nclass * p.acc_w;           // columns of one accumulator buffer
   const uint32_t t_ring = tmem_base + (uint32_t)(p.nbuf * acc_cols);   // A-operand ring: kRing slots of 64 columns (hi | lo)
   const bool timed = p.timing != nullptr;
-  const int steps_per_tile = p.k_chunks * p.nsteps;
+  // Programmatic dependent launch: from here on the next kernel of the stream may become resident (on SMs this grid has
+  // left).  This kernel's own prologue above ran while its predecessor was still draining; the roles that read what the
+  // predecessor wrote (A producer) or write global memory (epilogue) wait for it below, the W producer does not (weights
+  // are constants) and fills the weight ring in the meantime.
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===== A producer: one halo box per plane and 32-channel chunk ======================================================
@@ -342,6 +350,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
       long long w_aempty = 0;
       const long long t_begin = clock64();
       for (int i = 0; i < p.nplanes; ++i) a_bytes += (uint32_t)p.planes[i].bytes;
+      pdl_wait();   // the input is the previous kernel's output
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int nt, n, y0, x0;
         halo_decode_tile<PER_TAP>(p, tile, nt, n, y0, x0);
@@ -422,6 +431,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
     const int g8 = m >> 3, r = m & 7;
     const int ngroups = p.ngroups;
     long long w_safull = 0, w_free = 0;
+#ifdef DEMON_TC_TIMING_FULL
+    long long d_load = 0, d_store = 0, d_arrive = 0;
+#endif
     const long long t_begin = clock64();
     // The group visits only its OWN steps: global step gs = grp, grp + G, grp + 2G, ...; t_own is that step's index
     // inside the current chunk.  Ring slot and parity follow from gs; in per-tap mode so does the A stage (one per step).
@@ -444,6 +456,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
           const uint32_t use_cur = (gs >> 2) & 1u;
           const int sa_cur = sa;
           uint32_t row;
+#ifdef DEMON_TC_TIMING_FULL
+          const long long c0 = clock64();
+#endif
           if (PER_TAP) {
             wait_t(afull0 + 8 * sa_cur, pa, p.err, w_safull, timed);
             __syncwarp();
@@ -483,9 +498,15 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
               hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
             }
           }
+#ifdef DEMON_TC_TIMING_FULL
+          const long long c1 = clock64();
+#endif
           wait_t(free0 + 8 * slot_cur, use_cur ^ 1, p.err, w_free, timed);
           __syncwarp();
           tc_fence_after();
+#ifdef DEMON_TC_TIMING_FULL
+          const long long c2 = clock64();
+#endif
           const uint32_t taddr = t_ring + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot_cur * 64);
           tmem_st_x32(taddr, hi);
           if (MODE != 0) {
@@ -494,12 +515,18 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
             tmem_st_x32(taddr + 32, lo);
           }
           tmem_st_wait();
+#ifdef DEMON_TC_TIMING_FULL
+          const long long c3 = clock64();
+#endif
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
             mbar_arrive(full0 + 8 * slot_cur);
             if (PER_TAP) mbar_arrive(aempty0 + 8 * sa_cur);   // the shift's tile has been consumed: stage back to the producer
           }
+#ifdef DEMON_TC_TIMING_FULL
+          d_load += c1 - c0; d_store += c3 - c2; d_arrive += clock64() - c3;
+#endif
         }
         t_own -= nsteps;   // index of the next own step inside the NEXT chunk
         if (!PER_TAP) {
@@ -512,6 +539,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
     if (timed && lane == 0 && q == 0) {
       if (grp == 0) { p.timing[blockIdx.x * 16 + 6] = w_safull; p.timing[blockIdx.x * 16 + 4] = w_free; p.timing[blockIdx.x * 16 + 10] = clock64() - t_begin; }
       else if (grp == 1) p.timing[blockIdx.x * 16 + 12] = w_free;
+#ifdef DEMON_TC_TIMING_FULL
+      if (grp == 0) { p.timing[blockIdx.x * 16 + 13] = d_load; p.timing[blockIdx.x * 16 + 14] = d_store; p.timing[blockIdx.x * 16 + 15] = d_arrive; }
+#endif
     }
   } else if (warp < w_warp) {
     // ===== epilogue ======================================================================================================
@@ -538,6 +568,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
     long long w_cfull = 0;
     const long long t_begin = clock64();
     int it = 0;
+    pdl_wait();   // the output buffer may still be read (or written) by the previous kernel
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       int nt, n, y0, x0;
       halo_decode_tile<PER_TAP>(p, tile, nt, n, y0, x0);
@@ -952,7 +983,8 @@ static int launch_variant(const HaloPlan* plan, const HaloParams& prm, int grid,
     DEMON_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<PER_TAP, CIN8, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     ds.halo_attr_set |= 1u << slot;
   }
-  conv_tc_halo_kernel<PER_TAP, CIN8, MODE><<<grid, threads, plan->smem_bytes, stream>>>(plan->maps, prm);
+  cudaError_t le = launch_pdl(conv_tc_halo_kernel<PER_TAP, CIN8, MODE>, dim3(grid), dim3(threads), (size_t)plan->smem_bytes, stream, plan->maps, prm);
+  if (le != cudaSuccess) return fail(DEMON_E_CUDA, "conv_tc_halo launch: %s", cudaGetErrorString(le));
   DEMON_LAUNCH_CHECK();
   return DEMON_OK;
 }

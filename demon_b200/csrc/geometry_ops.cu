@@ -4,6 +4,7 @@
 // dimension on threadIdx.x so every warp reads and writes whole 128-byte lines, grids sized from the
 // tensor (they are far larger than 148 SMs at the benchmark sizes), no shared memory except the
 // per-sample camera.
+#include <cstdlib>
 #include "geometry.cuh"
 
 namespace demon {
@@ -13,6 +14,14 @@ std::string& last_error_ref() {
   return s;
 }
 std::atomic<int64_t> g_launch_count{0};
+
+bool pdl_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("DEMON_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 
 int fail(int code, const char* fmt, ...) {
   char buf[1024];
@@ -88,7 +97,7 @@ __global__ void __launch_bounds__(128) warp2d_kernel(const T* __restrict__ in, c
 // fewer than 2^31 elements, W is a multiple of 4 and the base pointers are 16-byte aligned), and the sixteen gathers of
 // a channel are in flight before the first blend.  Per-pixel arithmetic is the same sequence of IEEE operations as in
 // warp2d_kernel (bit exact with the reference's CPU kernel, warp2d.cc:186-247).
-template <bool CLAMP>
+template <bool CLAMP, int CU>   // CU channels per round: all their gathers (16 per channel) are in flight before the first blend
 __global__ void __launch_bounds__(128) warp2d_v4_kernel(const float* __restrict__ in, const float* __restrict__ disp,
                                                        float* __restrict__ out, int C, int H, int W, bool normalized, float border_value) {
   const int x = (blockIdx.x * 128 + threadIdx.x) * 4;
@@ -120,15 +129,23 @@ __global__ void __launch_bounds__(128) warp2d_v4_kernel(const float* __restrict_
   }
   const float* src = in + n * C * hw;
   float* dst = out + n * C * hw + row;
-  for (int c = 0; c < C; ++c, src += hw, dst += hw) {
-    float v[4][4];
+  for (int c = 0; c < C; c += CU, src += CU * hw, dst += CU * hw) {   // (the launcher guarantees C % CU == 0)
+    float v[CU][4][4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (CLAMP || valid[k]) { v[k][0] = __ldg(src + o00[k]); v[k][1] = __ldg(src + o01[k]); v[k][2] = __ldg(src + o10[k]); v[k][3] = __ldg(src + o11[k]); }
-    float r[4];
+    for (int u = 0; u < CU; ++u)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) r[k] = (CLAMP || valid[k]) ? warp2d_blend(v[k][0], v[k][1], v[k][2], v[k][3], t[k]) : border_value;
-    *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
+      for (int k = 0; k < 4; ++k)
+        if (CLAMP || valid[k]) {
+          const float* q = src + u * hw;
+          v[u][k][0] = __ldg(q + o00[k]); v[u][k][1] = __ldg(q + o01[k]); v[u][k][2] = __ldg(q + o10[k]); v[u][k][3] = __ldg(q + o11[k]);
+        }
+#pragma unroll
+    for (int u = 0; u < CU; ++u) {
+      float r[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) r[k] = (CLAMP || valid[k]) ? warp2d_blend(v[u][k][0], v[u][k][1], v[u][k][2], v[u][k][3], t[k]) : border_value;
+      *reinterpret_cast<float4*>(dst + u * hw) = make_float4(r[0], r[1], r[2], r[3]);
+    }
   }
 }
 
@@ -141,8 +158,10 @@ bool warp2d_fast<float>(const float* in, const float* disp, float* out, int n, i
   if ((w & 3) != 0 || w < 128 || total >= (1ll << 31) || ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(disp) | reinterpret_cast<uintptr_t>(out)) & 15) != 0)
     return false;
   dim3 grid(ceil_div(w / 4, 128), h, n), block(128);
-  if (border_mode == DEMON_BORDER_CLAMP) warp2d_v4_kernel<true><<<grid, block, 0, s>>>(in, disp, out, c, h, w, normalized != 0, border_value);
-  else warp2d_v4_kernel<false><<<grid, block, 0, s>>>(in, disp, out, c, h, w, normalized != 0, border_value);
+  // (CU = 3, all gathers of an RGB image in flight at once, was measured slower: 128 registers, 22 % occupancy, 77 us
+  // against 62 us at [8,3,768,1024]; one channel per round keeps 48 registers)
+  if (border_mode == DEMON_BORDER_CLAMP) warp2d_v4_kernel<true, 1><<<grid, block, 0, s>>>(in, disp, out, c, h, w, normalized != 0, border_value);
+  else warp2d_v4_kernel<false, 1><<<grid, block, 0, s>>>(in, disp, out, c, h, w, normalized != 0, border_value);
   return true;
 }
 
@@ -215,19 +234,19 @@ __global__ void __launch_bounds__(256) depth_to_flow_v4_kernel(const float* __re
                                                               bool inverse_depth, bool normalize_flow) {
   __shared__ D2FCamera<float> cam;
   const int n = blockIdx.y;
-  if (threadIdx.x == 0)
-    d2f_camera(cam, intrinsics + 4 * n, rotation + (size_t)n * rotation_step(rotation_format), translation + 3 * n, rotation_format, W, H);
-  __syncthreads();
   const int hw = H * W;
   const float* dn = depth + n * hw;
   float* fn = flow + n * 2 * hw;
   float4 dv[2];
   int idx[2];
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < 2; ++k) {   // the depth loads are in flight while thread 0 sets the camera up
     idx[k] = ((blockIdx.x * 2 + k) * 256 + threadIdx.x) * 4;
     dv[k] = (idx[k] < hw) ? __ldg(reinterpret_cast<const float4*>(dn + idx[k])) : make_float4(1.f, 1.f, 1.f, 1.f);
   }
+  if (threadIdx.x == 0)
+    d2f_camera(cam, intrinsics + 4 * n, rotation + (size_t)n * rotation_step(rotation_format), translation + 3 * n, rotation_format, W, H);
+  __syncthreads();
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     if (idx[k] >= hw) continue;
@@ -405,14 +424,43 @@ __global__ void __launch_bounds__(128) median3x3_v4_kernel(const float* __restri
     r[dy][5] = b.x; r[dy][6] = b.y; r[dy][7] = b.z; r[dy][8] = b.w;
   }
   float m[4];
+  // Which ELEMENT the reference's selection passes pick only matters when two candidates compare equal without being
+  // the same bits (+0 / -0) or do not compare at all (NaN).  Without such values among the 27 inputs the result is simply
+  // the median VALUE, and any median network returns the same bits: sort the nine columns once (the four windows share
+  // three of them), then median(max of the minima, median of the middles, min of the maxima): ~26 min/max per output
+  // instead of 30 compare + 2 selects.  Otherwise: the reference's order, compare for compare.
+  bool special = false;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float v[9];
+  for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
+    for (int c = 0; c < 9; ++c) special |= !(fabsf(r[dy][c]) > 0.f);
+  if (!special) {
+    float lo[9], mid[9], hi[9];
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) v[3 * dy + dx] = r[dy][2 * j + dx];
-    m[j] = median9_reference_order(v);
+    for (int c = 0; c < 9; ++c) {
+      const float t1 = fminf(r[0][c], r[1][c]), t2 = fmaxf(r[0][c], r[1][c]);
+      lo[c] = fminf(t1, r[2][c]);
+      hi[c] = fmaxf(t2, r[2][c]);
+      mid[c] = fmaxf(t1, fminf(t2, r[2][c]));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = 2 * j;
+      const float a = fmaxf(fmaxf(lo[c], lo[c + 1]), lo[c + 2]);
+      const float b = fmaxf(fminf(mid[c], mid[c + 1]), fminf(fmaxf(mid[c], mid[c + 1]), mid[c + 2]));
+      const float d = fminf(fminf(hi[c], hi[c + 1]), hi[c + 2]);
+      m[j] = fmaxf(fminf(a, b), fminf(fmaxf(a, b), d));
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v[9];
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) v[3 * dy + dx] = r[dy][2 * j + dx];
+      m[j] = median9_reference_order(v);
+    }
   }
   *reinterpret_cast<float4*>(out + z * (Ho * Wo) + yo * Wo + xo) = make_float4(m[0], m[1], m[2], m[3]);
 }

@@ -441,6 +441,8 @@ int run_range(demon_net* n, const std::string& first, const std::string& last, c
 // strided element copy: dst[n*dn + p*dp + c*dc] = src[n*sn + p*sp + c*sc], c fastest
 __global__ void __launch_bounds__(256) strided_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int P, int C,
                                                           long sn, long sp, long sc, long dn, long dp, long dc) {
+  pdl_launch_dependents();   // common.cuh: programmatic dependent launch
+  pdl_wait();
   const long total = (long)N * P * C;
   for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
     const int c = (int)(i % C);
@@ -457,7 +459,7 @@ int strided_copy(const float* src, float* dst, int N, int P, int C, long sn, lon
   if (total == 0) return DEMON_OK;
   long blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  strided_copy_kernel<<<(int)blocks, 256, 0, stream>>>(src, dst, N, P, C, sn, sp, sc, dn, dp, dc);
+  (void)launch_pdl(strided_copy_kernel, dim3((int)blocks), dim3(256), 0, stream, src, dst, N, P, C, sn, sp, sc, dn, dp, dc);
   DEMON_LAUNCH_CHECK();
   return DEMON_OK;
 }
@@ -466,6 +468,8 @@ int strided_copy(const float* src, float* dst, int N, int P, int C, long sn, lon
 // examples/evaluation.py:170-173)
 __global__ void __launch_bounds__(128) median_planes_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int H, int W,
                                                            int Ho, int Wo, long in_sn, long out_sn) {
+  pdl_launch_dependents();   // common.cuh: programmatic dependent launch
+  pdl_wait();
   const int xo = blockIdx.x * 128 + threadIdx.x;
   const int yo = blockIdx.y;
   const int n = blockIdx.z / C, c = blockIdx.z % C;
@@ -485,6 +489,8 @@ __global__ void __launch_bounds__(128) median_planes_kernel(const float* __restr
 // [warped(3), flow(2), depth(1), normal(3), 0, 0, 0].  dn2 = [depth, normal] NHWC4, motion [B,8] = rot|trans|scale.
 __global__ void __launch_bounds__(256) flow_extra_kernel(const float* __restrict__ dn2, const float* __restrict__ motion,
                                                         const float* __restrict__ image2_2, float* __restrict__ extra, int H, int W) {
+  pdl_launch_dependents();   // common.cuh: programmatic dependent launch
+  pdl_wait();
   __shared__ D2FCamera<float> cam;
   const int n = blockIdx.y;
   if (threadIdx.x == 0) {
@@ -523,6 +529,8 @@ __global__ void __launch_bounds__(256) flow_extra_kernel(const float* __restrict
 __global__ void __launch_bounds__(128) dm_extra_kernel(const float* __restrict__ flowconf2, const float* __restrict__ motion_prev,
                                                       const float* __restrict__ image2_2, float* __restrict__ extra, int H, int W,
                                                       int extra_pitch, bool with_depth) {
+  pdl_launch_dependents();   // common.cuh: programmatic dependent launch
+  pdl_wait();
   __shared__ F2DCamera cam;
   const int n = blockIdx.y;
   if (with_depth && threadIdx.x == 0) {
@@ -558,6 +566,8 @@ __global__ void __launch_bounds__(128) dm_extra_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) refine_input_kernel(const float* __restrict__ image1, long img_sn, long img_sp, long img_sc,
                                                           const float* __restrict__ depth, long d_sn, long d_sp, float* __restrict__ rin,
                                                           int N, int H, int W, int h, int w) {
+  pdl_launch_dependents();   // common.cuh: programmatic dependent launch
+  pdl_wait();
   const long total = (long)N * H * W;
   for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
     const int x = (int)(i % W);
@@ -580,6 +590,8 @@ __global__ void __launch_bounds__(256) refine_input_kernel(const float* __restri
 // Same two IEEE operations as numpy's float32 expression, so the result equals the fp32 entry bit for bit.
 __global__ void __launch_bounds__(256) u8_import_kernel(const unsigned char* __restrict__ images, float* __restrict__ img8,
                                                        float* __restrict__ planes2, int B, int P) {
+  pdl_launch_dependents();   // common.cuh: programmatic dependent launch
+  pdl_wait();
   const long total = (long)B * P;
   for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
     const int n = (int)(i / P), p = (int)(i - (long)n * P);
@@ -602,6 +614,8 @@ __global__ void __launch_bounds__(256) u8_import_kernel(const unsigned char* __r
 
 // image2_2 given as uint8 [B,h,w,3] (examples/example.py:22: the PIL-resized second image) -> NCHW fp32 planes
 __global__ void __launch_bounds__(256) u8_planes_kernel(const unsigned char* __restrict__ img, float* __restrict__ planes, int B, int P) {
+  pdl_launch_dependents();   // common.cuh: programmatic dependent launch
+  pdl_wait();
   const long total = (long)B * P;
   for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
     const int n = (int)(i / P), p = (int)(i - (long)n * P);
@@ -633,9 +647,9 @@ int import_image2_2(demon_net* n, const float* image2_2, int data_format, cudaSt
 // planes: image 2 as NCHW fp32 planes, `sn` floats between samples (6*P inside an image pair, 3*P for a packed copy)
 int median_image2_2(demon_net* n, const float* planes, long sn, cudaStream_t s) {
   const int B = n->B;
-  median_planes_kernel<<<dim3(1, 96, B * 3), 128, 0, s>>>(planes, n->i22_half->p, 3, 192, 256, 96, 128, sn, 3L * 96 * 128);
+  (void)launch_pdl(median_planes_kernel, dim3(dim3(1, 96, B * 3)), dim3(128), 0, s, planes, n->i22_half->p, 3, 192, 256, 96, 128, sn, 3L * 96 * 128);
   DEMON_LAUNCH_CHECK();
-  median_planes_kernel<<<dim3(1, 48, B * 3), 128, 0, s>>>(n->i22_half->p, n->i22->p, 3, 96, 128, 48, 64, 3L * 96 * 128, 3L * 48 * 64);
+  (void)launch_pdl(median_planes_kernel, dim3(dim3(1, 48, B * 3)), dim3(128), 0, s, n->i22_half->p, n->i22->p, 3, 96, 128, 48, 64, 3L * 96 * 128, 3L * 48 * 64);
   DEMON_LAUNCH_CHECK();
   return DEMON_OK;
 }
@@ -667,7 +681,7 @@ int run_flow_block(demon_net* n, const std::string& scope, bool iterative, cudaS
   int rc;
   if (head && (rc = run_range(n, p + "conv1y", p + "conv2x", s))) return rc;
   if (iterative) {
-    flow_extra_kernel<<<dim3(ceil_div(48 * 64, 256), n->B), 256, 0, s>>>(n->dn2->p, n->motion->p, n->i22->p, n->extra_in->p, 48, 64);
+    (void)launch_pdl(flow_extra_kernel, dim3(dim3(ceil_div(48 * 64, 256), n->B)), dim3(256), 0, s, n->dn2->p, n->motion->p, n->i22->p, n->extra_in->p, 48, 64);
     DEMON_LAUNCH_CHECK();
     if ((rc = run_range(n, p + "conv2_extra_inputsy", p + "conv2_extra_inputsx", s))) return rc;
   }
@@ -679,7 +693,7 @@ int run_dm_block(demon_net* n, const std::string& scope, bool iterative, cudaStr
   int rc;
   if (head && (rc = run_range(n, p + "conv1y", p + "conv2x", s))) return rc;
   // the previous motion is still in n->motion here: this block's motion_fc3 overwrites it later
-  dm_extra_kernel<<<dim3(ceil_div(48 * 64, 128), n->B), 128, 0, s>>>(n->flowconf2->p, n->motion->p, n->i22->p, n->extra_in->p, 48, 64,
+  (void)launch_pdl(dm_extra_kernel, dim3(dim3(ceil_div(48 * 64, 128), n->B)), dim3(128), 0, s, n->flowconf2->p, n->motion->p, n->i22->p, n->extra_in->p, 48, 64,
                                                                    n->extra_in->C, iterative);
   DEMON_LAUNCH_CHECK();
   return run_range(n, p + "conv2_extra_inputsy", p + "predict_depthnormal2/conv2", s);
@@ -690,7 +704,7 @@ int run_refine_block(demon_net* n, const float* image1, long img_sn, long img_sp
   const long total = (long)n->B * n->RH * n->RW;
   long blocks = (total + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  refine_input_kernel<<<(int)blocks, 256, 0, s>>>(image1, img_sn, img_sp, img_sc, depth, d_sn, d_sp, n->rin->p, n->B, n->RH, n->RW, dh, dw);
+  (void)launch_pdl(refine_input_kernel, dim3((int)blocks), dim3(256), 0, s, image1, img_sn, img_sp, img_sc, depth, d_sn, d_sp, n->rin->p, n->B, n->RH, n->RW, dh, dw);
   DEMON_LAUNCH_CHECK();
   // the last layer writes straight into the caller's output (C = 1: NHWC == NCHW)
   Layer* last = n->by_name["netRefine/predict_depth0/conv2"];
@@ -975,11 +989,11 @@ static int pipeline_body(demon_net* n, const PipelineInput& in, int iterations, 
     float* planes2 = in.image2_2_u8 ? nullptr : n->c1y->p;
     long blocks = ((long)n->B * P + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    u8_import_kernel<<<(int)blocks, 256, 0, s>>>(in.images_u8, n->img8->p, planes2, n->B, (int)P);
+    (void)launch_pdl(u8_import_kernel, dim3((int)blocks), dim3(256), 0, s, in.images_u8, n->img8->p, planes2, n->B, (int)P);
     DEMON_LAUNCH_CHECK();
     if (in.image2_2_u8) {
       long b2 = ((long)n->B * 48 * 64 + 255) / 256;
-      u8_planes_kernel<<<(int)b2, 256, 0, s>>>(in.image2_2_u8, n->i22->p, n->B, 48 * 64);
+      (void)launch_pdl(u8_planes_kernel, dim3((int)b2), dim3(256), 0, s, in.image2_2_u8, n->i22->p, n->B, 48 * 64);
       DEMON_LAUNCH_CHECK();
     } else if ((rc = median_image2_2(n, planes2, 3 * P, s))) {
       return rc;
@@ -1182,6 +1196,9 @@ int demon_debug_describe_conv(int B, int H, int W, int Cin, int in_pitch, int Co
 }
 
 // ---- standalone convolution entries (tests) ---------------------------------------------------
+static double g_last_conv_ms = -1.0;
+double demon_debug_last_conv_ms(void) { return g_last_conv_ms; }
+
 static int standalone_conv(const float* in, float* out, int B, int H, int W, int Cin, int Cout, int kh, int kw, int sy, int sx,
                            const float* kernel_host, const float* bias_host, int leaky, int precision, bool deconv, void* stream) {
   DEMON_REQUIRE(in && out && kernel_host && bias_host, "conv: null pointer");
@@ -1224,8 +1241,15 @@ static int standalone_conv(const float* in, float* out, int B, int H, int W, int
     if (rc) return rc;
     l.use_tc = true;
   }
+  cudaEvent_t ev0, ev1;
+  cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+  cudaEventRecord(ev0, (cudaStream_t)stream);
   rc = run_layer(l, B, (cudaStream_t)stream);
+  cudaEventRecord(ev1, (cudaStream_t)stream);
   cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  float ms = -1.f;
+  if (e == cudaSuccess && cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) g_last_conv_ms = ms;
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1);
   for (void* q : tmp.dev_allocs) cudaFree(q);
   tc_layer_free(l.tc);
   if (rc) return rc;

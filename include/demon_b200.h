@@ -259,6 +259,10 @@ int demon_debug_describe_layers(const demon_net* net, char* buf, int buflen);
 int demon_debug_describe_conv(int B, int H, int W, int Cin, int in_pitch, int Cout, int out_pitch, int kh, int kw, int sy, int sx,
                               int deconv, int precision, char* buf, int buflen);
 
+/* debug: device time (CUDA events on the launching stream) of the kernel launches of the last demon_conv2d_nhwc /
+ * demon_deconv4x4s2_nhwc call, in milliseconds (weight packing and uploads excluded); < 0 if none was timed */
+double demon_debug_last_conv_ms(void);
+
 /* Standalone convolution entry used by tests to compare the tcgen05 path with the fp32 SIMT path on
  * the same NHWC tensors.  in [B,H,W,Cin], kernel TF layout [kh,kw,cin,cout] (host), bias [cout] (host)
  * -> out [B,ceil(H/sy),ceil(W/sx),Cout]; caffe padding (helpers.py:70-94). */

@@ -67,6 +67,21 @@ def test_median_vector_path_bit_exact_with_nans_and_ties(ops, shape):
     assert np.array_equal(g[m].view(np.uint32), r[m].view(np.uint32))
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 256), (1, 2, 35, 512)])
+def test_median_vector_path_min_max_network_bit_exact(ops, shape):
+    """No NaN, no zero: the vector kernel takes its min/max network (sorted columns shared by the four windows) instead of
+    the reference's selection passes; the selected VALUE, hence the bits, must be the same -- heavy ties, both signs."""
+    rng = np.random.RandomState(7 + sum(shape))
+    A = (np.round(rng.rand(*shape) * 5) / 5 + 0.1).astype(np.float32) * rng.choice([-1.0, 1.0], size=shape).astype(np.float32)
+    assert not np.any(A == 0)
+    g, r = ops.median3x3_downsample(A), oops.median3x3_downsample(A)
+    assert np.array_equal(g.view(np.uint32), r.view(np.uint32))
+    B = rng.standard_normal(shape).astype(np.float32) * 1e-3
+    B[0, ..., :8] = np.float32(1e-42)   # subnormals compare and select like any other value
+    g, r = ops.median3x3_downsample(B), oops.median3x3_downsample(B)
+    assert np.array_equal(g.view(np.uint32), r.view(np.uint32))
+
+
 def test_median_twice_at_benchmark_size_matches_oracle(ops):
     rng = np.random.RandomState(1)
     img = rng.uniform(-0.5, 0.5, (8, 3, 192, 256)).astype(np.float32)

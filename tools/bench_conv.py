@@ -23,6 +23,11 @@ SHAPES = {
     "conv5_1y": ("conv", 64, 6, 8, 512, 512, 3, 1, 1, 1),
     "conv3x": ("conv", 64, 24, 64, 128, 128, 1, 5, 1, 2),
     "refine2_upconv": ("deconv", 64, 24, 32, 256, 64),
+    "refine3_upconv": ("deconv", 64, 12, 16, 544, 128),
+    "refine4_upconv": ("deconv", 64, 6, 8, 512, 256),
+    "conv2_1y": ("conv", 64, 48, 64, 64, 64, 3, 1, 1, 1),
+    "conv4x": ("conv", 64, 12, 32, 256, 256, 1, 5, 1, 2),
+    "conv5_1x": ("conv", 64, 6, 8, 512, 512, 1, 3, 1, 1),
 }
 
 
@@ -55,15 +60,16 @@ def main():
             _lib.check(lib.demon_deconv4x4s2_nhwc(x.data_ptr(), out.data_ptr(), B, H, W, Cin, Cout, k.ctypes.data, b.ctypes.data, 1, prec, stream))
     torch.cuda.synchronize()
     print(name, "done; timeouts", lib.demon_debug_tc_timeouts())
+    print("  kernel time of the last call: %.4f ms" % lib.demon_debug_last_conv_ms())
     if timing:
         buf = np.zeros((148, 16), np.int64)
         if lib.demon_debug_tc_timing(0, buf.ctypes.data, 148) == 0:
             names = ["A-producer wait A_empty", "W-producer wait W_empty", "MMA wait accum_empty", "MMA wait T_full", "stager0 wait T_empty",
                      "MMA wait W_full", "stager0 wait A_full", "epilogue wait accum_full", "A-producer total", "MMA total", "stager0 total",
-                     "epilogue total", "stager1 wait T_empty", "MMA thread: wait + fence + next poll", "MMA thread: descriptors + 8..12 tcgen05.mma", "MMA thread: commits"]
+                     "epilogue total", "stager1 wait T_empty", "stager0: address math + shared loads issued", "stager0: tcgen05.st x2 + split + wait::st", "stager0: fence + arrive"]
             m = buf.mean(axis=0)
             for i, nm in enumerate(names):
-                print("  %-28s %12.0f cycles (avg per CTA)" % (nm, m[i]))
+                print("  %-44s %12.0f cycles (avg per CTA)" % (nm, m[i]))
 
 
 if __name__ == "__main__":

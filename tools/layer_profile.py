@@ -1,4 +1,4 @@
-"""Per-layer device time of the full pipeline at batch 64 (CUDA events around every layer launch through the
+"""Per-layer device time of the full pipeline at batch 64 (or argv[3]) (CUDA events around every layer launch through the
 C ABI's demon_net_profile_* hooks).  Prints a table sorted by time and writes it as JSON."""
 import ctypes
 import json
@@ -15,7 +15,8 @@ from demon_b200.networks_original import Session, DemonPipeline
 def main():
     precision = sys.argv[1] if len(sys.argv) > 1 else "3xtf32"
     out_path = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "layers_%s.json" % precision)
-    B, steps = 64, 5
+    B = int(sys.argv[3]) if len(sys.argv) > 3 else 64
+    steps = 5
     lib = _lib.load()
     sess = Session(precision)
     sess.load_weights(W.synthetic_weights(0))
