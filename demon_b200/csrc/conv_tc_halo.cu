@@ -171,6 +171,10 @@ struct MmaCtx {
   uint32_t n_tile, acc_w;
   uint32_t idesc, idesc2;
   int* err;
+#ifdef DEMON_TC_TIMING_FULL
+  mutable long long* evlog;   // CTA 0: clock64 per event of the first 64 global steps (rows of 64 behind the wait counters)
+  mutable int ev_step;
+#endif
 };
 
 // all MMAs of ONE class block of a step: K = 32 as four K8 slices
@@ -217,11 +221,16 @@ template <int MODE, int SLOT, bool MULTI>
 __device__ __forceinline__ bool mma_step(const MmaCtx& c, uint32_t d_base, uint32_t par, uint32_t npar, bool rdy, bool fresh, uint32_t cm,
                                          uint32_t fm, long long& w_full) {
 #ifdef DEMON_TC_TIMING_FULL
-  if (!rdy) wait_t(c.full0 + 8 * SLOT, par, c.err, w_full, true);    // diagnostic build: every wait bracketed by clock reads
+  // diagnostic build: every wait bracketed by clock reads, and an event log of CTA 0's first 64 steps (tools/bench_conv.py prints it)
+  if (c.evlog && c.ev_step < 64) { c.evlog[512 + c.ev_step] = clock64(); c.evlog[576 + c.ev_step] = rdy ? 1 : 0; }   // step entered, early probe result
+  if (!rdy) wait_t(c.full0 + 8 * SLOT, par, c.err, w_full, true);
+  if (c.evlog && c.ev_step < 64) c.evlog[c.ev_step] = clock64();         // full[] of the step observed
+  tc_fence_after();
+  if (c.evlog && c.ev_step < 64) c.evlog[384 + c.ev_step] = clock64();   // after tcgen05.fence::after_thread_sync
 #else
   if (!rdy) wait_t(c.full0 + 8 * SLOT, par, c.err, w_full, false);   // (the MMA thread's waits are never bracketed: no clock reads on its fast path)
-#endif
   tc_fence_after();
+#endif
   const bool next_rdy = mbar_test(c.full0 + 8 * ((SLOT + 1) & (kRing - 1)), npar);
   const uint32_t a_hi = c.t_ring + (uint32_t)(SLOT * 64);
   uint32_t wb = c.w_ring + (uint32_t)SLOT * c.w_stage_bytes;
@@ -235,7 +244,14 @@ __device__ __forceinline__ bool mma_step(const MmaCtx& c, uint32_t d_base, uint3
         wb += c.cls_bytes;
       }
   }
+#ifdef DEMON_TC_TIMING_FULL
+  if (c.evlog && c.ev_step < 64) c.evlog[448 + c.ev_step] = clock64();   // the step's MMAs issued
+#endif
   umma_commit(c.free0 + 8 * SLOT);
+#ifdef DEMON_TC_TIMING_FULL
+  if (c.evlog && c.ev_step < 64) c.evlog[64 + c.ev_step] = clock64();    // the step's commit issued
+  ++c.ev_step;
+#endif
   return next_rdy;
 }
 
@@ -410,6 +426,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
       c.n_tile = (uint32_t)p.n_tile; c.acc_w = (uint32_t)p.acc_w;
       c.idesc = umma_idesc_tf32(p.n_tile); c.idesc2 = umma_idesc_tf32(2 * p.n_tile);
       c.err = p.err;
+#ifdef DEMON_TC_TIMING_FULL
+      c.evlog = (timed && blockIdx.x == 0) ? p.timing + 160 * 16 : nullptr;
+      c.ev_step = 0;
+#endif
       long long w_cempty = 0, w_full = 0;
       const long long t_begin = clock64();
       if (p.nclass == 1) mma_main_loop<MODE, false>(p, c, tmem_base, acc_cols, cfull0, cempty0, w_cempty, w_full);
@@ -506,6 +526,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
           tc_fence_after();
 #ifdef DEMON_TC_TIMING_FULL
           const long long c2 = clock64();
+          if (timed && blockIdx.x == 0 && q == 0 && lane == 0 && gs < 64) p.timing[160 * 16 + 128 + gs] = c2;   // free[] observed
 #endif
           const uint32_t taddr = t_ring + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot_cur * 64);
           tmem_st_x32(taddr, hi);
@@ -526,6 +547,11 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
           }
 #ifdef DEMON_TC_TIMING_FULL
           d_load += c1 - c0; d_store += c3 - c2; d_arrive += clock64() - c3;
+          if (timed && blockIdx.x == 0 && q == 0 && lane == 0 && gs < 64) {
+            p.timing[160 * 16 + 192 + gs] = clock64();   // arrived on full[]
+            p.timing[160 * 16 + 256 + gs] = c0;          // started on the step (address math, shared loads)
+            p.timing[160 * 16 + 320 + gs] = c3;          // tcgen05.wait::st returned
+          }
 #endif
         }
         t_own -= nsteps;   // index of the next own step inside the NEXT chunk

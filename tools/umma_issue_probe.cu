@@ -38,7 +38,7 @@ __device__ __forceinline__ void ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 
-struct Cfg { int mma_steps, n, st_warps, ld_warps, st_iters, ld_iters, st_per_iter, commits, polls, every, nacc, nthreads; };
+struct Cfg { int mma_steps, n, st_warps, ld_warps, st_iters, ld_iters, st_per_iter, commits, polls, every, nacc, nthreads, fence, a_base; };
 struct Out { long long mma_cycles, st_cycles, ld_cycles; long long st_done, ld_done; long long mma2_cycles; };
 
 __global__ void __launch_bounds__(480, 1) probe(const Cfg* cfgs, Out* outs, int ncfg, float* sink) {
@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(480, 1) probe(const Cfg* cfgs, Out* outs, int 
         const uint32_t acc0 = tmem + (uint32_t)(me * 128);   // accumulators of this thread: columns [me*128, me*128 + 128)
         const long long t0 = clock64();
         for (int s = 0; s < c.mma_steps; ++s) {
-          const uint32_t a_hi = tmem + 256 + (uint32_t)((s & 3) * 64), a_lo = a_hi + 32;
+          if (c.fence) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = tmem + (uint32_t)(c.a_base ? c.a_base : 256) + (uint32_t)((s & 3) * 64), a_lo = a_hi + 32;
           const uint32_t d = acc0 + (uint32_t)((c.nacc > 1 ? (s % c.nacc) : 0) * 2 * n);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -168,6 +169,12 @@ int main() {
     c.push_back({steps, n, 0, 0, 0, 0, 2, 1, 1, 2, 1, 2});   // two issuing threads, every second step
     c.push_back({steps, n, 8, 4, 0, 0, 2, 1, 1, 1, 1, 1});   // one thread, with st + ld traffic
     c.push_back({steps, n, 8, 4, 0, 0, 2, 1, 1, 1, 1, 2});   // two threads, with st + ld traffic
+    c.push_back({steps, n, 0, 0, 0, 0, 2, 1, 1, 1, 1, 1, 1});   // one thread, commit + poll + tcgen05.fence::after_thread_sync every step
+    c.push_back({steps, n, 0, 0, 0, 0, 2, 1, 1, 1, 1, 2, 1});   // two threads, the same
+    c.push_back({steps, n, 8, 4, 0, 0, 2, 1, 1, 1, 1, 1, 1});   // one thread, fence, with st + ld traffic
+    c.push_back({steps, n, 0, 0, 0, 0, 2, 0, 0, 1, 1, 2, 0, 64});    // two threads, MMAs alone, A ring right behind the accumulators (columns 64..319)
+    c.push_back({steps, n, 0, 0, 0, 0, 2, 1, 1, 1, 1, 2, 0, 64});    // ... with commit + poll
+    c.push_back({steps, n, 0, 0, 0, 0, 2, 1, 1, 1, 1, 1, 0, 64});    // one thread, commit + poll, A ring at 64
   }
   Cfg* dc; Out* dout; float* sink;
   cudaMalloc(&dc, c.size() * sizeof(Cfg));
@@ -184,8 +191,8 @@ int main() {
   cudaMemcpy(h.data(), dout, c.size() * sizeof(Out), cudaMemcpyDeviceToHost);
   for (size_t i = 0; i < h.size(); ++i) {
     const long long cyc = h[i].mma_cycles > h[i].mma2_cycles ? h[i].mma_cycles : h[i].mma2_cycles;
-    printf("N=%2d threads=%d accumulator sets=%d commit+poll=%d every %d step(s) st_warps=%d ld_warps=%d : %7.1f cycles per step (all %d steps of %d thread(s))\n",
-           c[i].n, c[i].nthreads, c[i].nacc, c[i].commits, c[i].every, c[i].st_warps, c[i].ld_warps, (double)cyc / (c[i].mma_steps * c[i].nthreads),
+    printf("N=%2d threads=%d accumulator sets=%d commit+poll=%d every %d step(s) fence=%d A ring at column %d st_warps=%d ld_warps=%d : %7.1f cycles per step (all %d steps of %d thread(s))\n",
+           c[i].n, c[i].nthreads, c[i].nacc, c[i].commits, c[i].every, c[i].fence, c[i].a_base ? c[i].a_base : 256, c[i].st_warps, c[i].ld_warps, (double)cyc / (c[i].mma_steps * c[i].nthreads),
            c[i].mma_steps * c[i].nthreads, c[i].nthreads);
   }
   return 0;
