@@ -314,11 +314,15 @@ def attach_traffic(roofline, dom):
         if not os.path.isfile(tpath):
             continue
         tj = json.load(open(tpath))
-        key = {2: "refine0_upconv", 1: "refine2_upconv", 3: "refine2_upconv"}.get(dom)
+        key = {2: "refine0_upconv", 1: "refine3_upconv", 3: "refine3_upconv"}.get(dom)
+        if key not in tj:
+            key = {2: "refine0_upconv", 1: "refine2_upconv", 3: "refine2_upconv"}.get(dom)
         if key in tj:
             roofline["traffic"] = {"bytes": tj[key], "launch": key,
                                    "algorithmic_bytes": {"refine0_upconv": 2 * 64 * 96 * 128 * 128 * 4 + 4 * 4 * 128 * 32 * 4,
-                                                         "refine2_upconv": 64 * 24 * 32 * 256 * 4 + 64 * 48 * 64 * 64 * 4}.get(key),
+                                                         "refine2_upconv": 64 * 24 * 32 * 256 * 4 + 64 * 48 * 64 * 64 * 4,
+                                                         # netFlow2/refine3/upconv: concat4 [64,12,16,576] in, [64,24,32,128] out, 4x4 kernel
+                                                         "refine3_upconv": 64 * 12 * 16 * 576 * 4 + 64 * 24 * 32 * 128 * 4 + 16 * 128 * 576 * 4}.get(key),
                                    "source": "profiles/%s (one launch at batch 64, dram__bytes_read.sum + dram__bytes_write.sum of an ncu --set full capture)" % fname}
             return
 

@@ -20,6 +20,8 @@ struct TcLayer {
   unsigned char tmap_host[128];
   int per_tap = 0;            // halo kernel in per-tap mode (low-resolution layers)
   void* halo_plan = nullptr;  // non-null: the layer runs on the halo kernel (conv_tc_halo.cu); owned
+  int ksplit = 1;             // halo kernel: K loop split over `ksplit` work items per tile; then the launch needs
+  size_t splitk_bytes = 0;    //   `splitk_bytes` of scratch in probs[0].partial (partial sums, reduced by a second kernel)
 };
 
 bool tc_layer_supported(const ConvProblem& p);

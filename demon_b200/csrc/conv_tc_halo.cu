@@ -75,6 +75,12 @@ struct HaloParams {
   int tiles_x, tiles_y, B, n_tiles, total_tiles;
   uint32_t mul_n_tiles, mul_tiles_x, mul_tiles_y;   // fast_div multipliers
   int k_chunks, nplanes, nsteps, nclass;
+  // split-K: a work ITEM is (tile, z), z < ksplit: kc_split = k_chunks / ksplit chunks of the tile's K loop, accumulated into
+  // partial buffer z (out + z * part_stride, bias-free, no activation); halo_splitk_reduce_kernel sums the buffers.
+  // ksplit == 1: an item is a tile and the epilogue writes the layer's output directly.
+  int ksplit, kc_split, total_items;
+  uint32_t mul_ksplit;
+  long long part_stride;
   int ngroups;                                      // stager groups (2 or 3)
   // per step (one input shift of one 32-channel chunk)
   int st_plane[kMaxTaps], st_aoff[kMaxTaps];        // halo mode: plane and byte offset of the shift's first pixel
@@ -260,14 +266,14 @@ __device__ __forceinline__ bool mma_step(const MmaCtx& c, uint32_t d_base, uint3
 template <int MODE, bool MULTI>
 __device__ __forceinline__ void mma_main_loop(const HaloParams& p, const MmaCtx& c, uint32_t tmem_base, int acc_cols, uint32_t cfull0,
                                               uint32_t cempty0, long long& w_cempty, long long& w_full) {
-  const int steps_per_tile = p.k_chunks * p.nsteps;
+  const int steps_per_tile = p.kc_split * p.nsteps;   // steps of one work item
   const int nsteps = p.nsteps;
   const int nbuf = p.nbuf;
   uint64_t cmasks = 0, fmasks = 0;   // class / fresh masks of the steps of a chunk, four bits per step (MULTI only)
   if (MULTI)
     for (int t = 0; t < nsteps; ++t) { cmasks |= (uint64_t)p.st_cmask[t] << (4 * t); fmasks |= (uint64_t)p.st_fmask[t] << (4 * t); }
-  int tile = blockIdx.x;
-  if (tile >= p.total_tiles) return;
+  int tile = blockIdx.x;                               // (work item index)
+  if (tile >= p.total_items) return;
   int it = 0, l = 0, t = 0;
   uint32_t par = 0;
   wait_t(cempty0, 1u, c.err, w_cempty, false);          // accumulator buffer 0, first use
@@ -287,7 +293,7 @@ __device__ __forceinline__ void mma_main_loop(const HaloParams& p, const MmaCtx&
     if (++l == steps_per_tile) {                                                                                          \
       umma_commit(cfull_bar);   /* the tile's accumulators are complete once everything issued so far has retired */      \
       tile += gridDim.x;                                                                                                  \
-      if (tile >= p.total_tiles) return;                                                                                  \
+      if (tile >= p.total_items) return;                                                                                  \
       ++it;                                                                                                               \
       l = 0;                                                                                                              \
       const int a = (nbuf == 2) ? (it & 1) : 0;                                                                           \
@@ -367,10 +373,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
       const long long t_begin = clock64();
       for (int i = 0; i < p.nplanes; ++i) a_bytes += (uint32_t)p.planes[i].bytes;
       pdl_wait();   // the input is the previous kernel's output
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const int tile = fast_div(item, p.ksplit, p.mul_ksplit);
+        const int kc0 = (item - tile * p.ksplit) * p.kc_split;
         int nt, n, y0, x0;
         halo_decode_tile<PER_TAP>(p, tile, nt, n, y0, x0);
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
+        for (int kc = kc0; kc < kc0 + p.kc_split; ++kc) {
           if (PER_TAP) {
             for (int t = 0; t < p.nsteps; ++t) {
               wait_t(aempty0 + 8 * sa, pa ^ 1, p.err, w_aempty, timed);
@@ -402,10 +410,12 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
       int slot = 0;
       uint32_t use = 0;
       long long w_free = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const int tile = fast_div(item, p.ksplit, p.mul_ksplit);
+        const int kc0 = (item - tile * p.ksplit) * p.kc_split;
         const int nt = tile - fast_div(tile, p.n_tiles, p.mul_n_tiles) * p.n_tiles;
-        const unsigned char* wsrc = p.w + (size_t)nt * p.k_chunks * p.w_chunk_bytes;
-        for (int kc = 0; kc < p.k_chunks; ++kc, wsrc += p.w_chunk_bytes) {
+        const unsigned char* wsrc = p.w + ((size_t)nt * p.k_chunks + kc0) * p.w_chunk_bytes;
+        for (int kc = 0; kc < p.kc_split; ++kc, wsrc += p.w_chunk_bytes) {
           for (int t = 0; t < p.nsteps; ++t) {
             wait_t(free0 + 8 * slot, use ^ 1, p.err, w_free, timed);
             const uint32_t bytes = (uint32_t)p.st_wbytes[t];
@@ -462,8 +472,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
     int sa = PER_TAP ? (grp % p.sa) : 0;          // halo mode: stage of the current chunk; per-tap: stage of step gs
     uint32_t pa = PER_TAP ? (uint32_t)((grp / p.sa) & 1) : 0u;
     const int nsteps = p.nsteps;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      for (int kc = 0; kc < p.k_chunks; ++kc) {
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      for (int kc = 0; kc < p.kc_split; ++kc) {
         uint32_t abase = 0;
         if (!PER_TAP) {
           wait_t(afull0 + 8 * sa, pa, p.err, w_safull, timed);
@@ -595,7 +605,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
     const long long t_begin = clock64();
     int it = 0;
     pdl_wait();   // the output buffer may still be read (or written) by the previous kernel
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+      const int tile = fast_div(item, p.ksplit, p.mul_ksplit);
+      const int z = item - tile * p.ksplit;
       int nt, n, y0, x0;
       halo_decode_tile<PER_TAP>(p, tile, nt, n, y0, x0);
       const int a = (p.nbuf == 2) ? (it & 1) : 0;
@@ -612,7 +624,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
           if (y0 + yl < p.Ho && x0 + xl < p.Wo && n + nl < p.B) rowmask |= 1u << i;
         }
       }
-      float* tile_out = p.out + ((size_t)(n * p.Hfull + y0 * p.osy) * p.Wfull + x0 * p.osx) * p.out_pitch;
+      float* tile_out = p.out + (size_t)z * p.part_stride + ((size_t)(n * p.Hfull + y0 * p.osy) * p.Wfull + x0 * p.osx) * p.out_pitch;
       const int cbase = nt * p.n_tile;
       for (int cls = 0; cls < p.nclass; ++cls) {
         float* cls_out = tile_out + (size_t)(p.cls_ooy[cls] * p.Wfull + p.cls_oox[cls]) * p.out_pitch;
@@ -644,7 +656,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
           __syncwarp();
           const int col = cbase + c0 + 4 * chunk;
           if (4 * chunk < ncol && col < p.Cout) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+            const float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);   // (null: split-K partial sums)
             float* colp = cls_out + col;
             const uint32_t sbase = stg + (uint32_t)(sub * kEpiRowBytes + chunk * 16);
 #pragma unroll
@@ -673,6 +685,31 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
   }
 }
 
+// Split-K second pass: out[pix][c] = act(bias[c] + sum_z part[z][pix][c]); the partial buffers have the geometry of the
+// layer's full output image ([B][Hfull][Wfull][cpitch] floats each), so sub-pixel classes are already interleaved.
+__global__ void __launch_bounds__(256) halo_splitk_reduce_kernel(const float* __restrict__ part, long long part_stride, int ksplit,
+                                                                 float* __restrict__ out, int out_pitch, int cpitch, int Cout, long long npix,
+                                                                 const float* __restrict__ bias, int leaky) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int c4n = cpitch >> 2;
+  const long long total = npix * c4n;
+  const float slope = leaky ? 0.1f : 1.0f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const long long pix = i / c4n;
+    const int c = (int)(i - pix * c4n) * 4;
+    if (c >= Cout) continue;
+    float4 acc = __ldg(reinterpret_cast<const float4*>(bias + c));
+    for (int z = 0; z < ksplit; ++z) {   // fixed order: deterministic
+      const float4 v = *reinterpret_cast<const float4*>(part + (size_t)z * part_stride + (size_t)pix * cpitch + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    acc.x = fmaxf(slope * acc.x, acc.x); acc.y = fmaxf(slope * acc.y, acc.y);
+    acc.z = fmaxf(slope * acc.z, acc.z); acc.w = fmaxf(slope * acc.w, acc.w);
+    *reinterpret_cast<float4*>(out + (size_t)pix * out_pitch + c) = acc;
+  }
+}
+
 int floor_div_h(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
 }  // namespace
@@ -696,6 +733,16 @@ static int stager_groups() {
     return (v < 1 || v > kMaxGroups) ? 2 : v;
   }();
   return g;
+}
+
+static bool splitk_enabled() {   // DEMON_TC_SPLITK=0: never split the K loop of a tensor-core layer (A/B measurements)
+  static const bool v = []() { const char* e = getenv("DEMON_TC_SPLITK"); return !(e && e[0] == '0'); }();
+  return v;
+}
+
+static bool wave_model_enabled() {   // DEMON_WAVE_MODEL=0: N tile by width alone (A/B measurements)
+  static const bool v = []() { const char* e = getenv("DEMON_WAVE_MODEL"); return !(e && e[0] == '0'); }();
+  return v;
 }
 
 // Steps of one chunk: the distinct input shifts of all classes, each with the mask of the classes that use it.
@@ -825,6 +872,14 @@ static bool halo_build(const ConvProblem* probs, int nclass, int nsplit, HaloPla
     while (n_tile > 16 && nclass * n_tile + ring_cols > 512) n_tile = (n_tile > 32) ? (n_tile / 2 + 15) / 16 * 16 : n_tile - 16;
     // narrow the N tile (down to 64) while the layer would leave SMs idle
     while (n_tile >= 128 && (n_tile % 32) == 0 && (long)m_tiles * ceil_div(p.Cout, n_tile) < 148) n_tile /= 2;
+    // wave quantisation: a persistent grid of 148 CTAs needs ceil(tiles / 148) rounds.  A step costs ~800 cycles at N = 128
+    // (three-instruction 3xTF32) and ~470 at N = 64 (stacked): e.g. 192 tiles of N = 128 take 2 rounds x 800, the same layer
+    // as 384 tiles of N = 64 takes 3 x 470.  Pick the cheaper (single-class 3xTF32 layers; measured per-step costs).
+    if (wave_model_enabled() && nsplit == 3 && nclass == 1 && n_tile == 128 && p.Cout % 64 == 0) {
+      const long t128 = (long)m_tiles * ceil_div(p.Cout, 128), t64 = (long)m_tiles * ceil_div(p.Cout, 64);
+      const long c128 = ((t128 + 147) / 148) * 800, c64 = ((t64 + 147) / 148) * 470;
+      if (c64 * 100 < c128 * 95) n_tile = 64;
+    }
     if (n_tile < 16 || nclass * n_tile + ring_cols > 512) return false;
     prm.mode = (nsplit == 1) ? 0 : 2;
     if (nsplit == 3 && n_tile <= 64 && nclass * 2 * n_tile + ring_cols <= 512) prm.mode = 1;
@@ -860,8 +915,29 @@ static bool halo_build(const ConvProblem* probs, int nclass, int nsplit, HaloPla
   prm.B = p.B;
   const int m_tiles = prm.tiles_x * prm.tiles_y * prm.tiles_b;
   prm.total_tiles = m_tiles * prm.n_tiles;
+  // ---- split-K: layers with few tiles and a long K loop (the 6x8 / 12x16 levels; everything at batch 1) leave most SMs
+  // idle and run their K loop serially.  Cost model in cycles: rounds of 148 items x (steps of an item x ~600 + ~3000 of
+  // prologue / epilogue), + ~12000 for the second pass; a split has to win 10 %.
+  prm.ksplit = 1;
+  if (splitk_enabled() && !prm.cin8 && prm.k_chunks >= 4) {
+    auto cost = [&](int ks) {
+      const long items = (long)prm.total_tiles * ks;
+      return ((items + 147) / 148) * ((long)(prm.k_chunks / ks) * prm.nsteps * 600 + 3000) + (ks > 1 ? 12000 : 0);
+    };
+    long best = cost(1);
+    for (int ks = 2; ks <= 8; ++ks) {
+      if (prm.k_chunks % ks != 0 || prm.k_chunks / ks < 2) continue;
+      const long c = cost(ks);
+      if (c * 10 < best * 9 && c < cost(prm.ksplit)) prm.ksplit = ks;
+    }
+  }
+  prm.kc_split = prm.k_chunks / prm.ksplit;
+  prm.total_items = prm.total_tiles * prm.ksplit;
+  prm.part_stride = 0;
   auto fd = [](int d) { return d <= 1 ? 0u : (uint32_t)((1ull << 32) / (uint64_t)d + 1ull); };
   prm.mul_n_tiles = fd(prm.n_tiles); prm.mul_tiles_x = fd(prm.tiles_x); prm.mul_tiles_y = fd(prm.tiles_y);
+  prm.mul_ksplit = fd(prm.ksplit);
+  if ((uint64_t)prm.total_items * (uint64_t)prm.ksplit >= (1ull << 32)) return false;
   if ((uint64_t)prm.total_tiles * (uint64_t)std::max(prm.n_tiles, std::max(prm.tiles_x, prm.tiles_y)) >= (1ull << 32)) return false;
   prm.out = p.out; prm.out_pitch = p.out_pitch; prm.Ho = p.Ho; prm.Wo = p.Wo; prm.Hfull = p.Hfull; prm.Wfull = p.Wfull;
   prm.osy = p.osy; prm.osx = p.osx; prm.Cout = p.Cout; prm.bias = p.bias; prm.leaky = p.leaky;
@@ -911,9 +987,9 @@ int tc_halo_describe(const ConvProblem* probs, int nclass, int nsplit, char* buf
   HaloPlan plan;
   if (!halo_build(probs, nclass, nsplit, plan, false)) return snprintf(buf, buflen, "halo: unsupported");
   const HaloParams& q = plan.prm;
-  int n = snprintf(buf, buflen, "halo %s mode %d n_tile %d x%d nbuf %d tmem %d steps %d x %d chunks sa %d a_stage %d w_slot %d smem %d tiles %d groups %d |",
+  int n = snprintf(buf, buflen, "halo %s mode %d n_tile %d x%d nbuf %d tmem %d steps %d x %d chunks sa %d a_stage %d w_slot %d smem %d tiles %d groups %d ksplit %d |",
                    q.per_tap ? "per-tap" : (q.cin8 ? "cin8" : "halo"), q.mode, q.n_tile, q.n_tiles, q.nbuf, q.tmem_cols, q.nsteps, q.k_chunks, q.sa,
-                   q.a_region_bytes, q.w_stage_bytes, plan.smem_bytes, q.total_tiles, q.ngroups);
+                   q.a_region_bytes, q.w_stage_bytes, plan.smem_bytes, q.total_tiles, q.ngroups, q.ksplit);
   for (int t = 0; t < q.nsteps && n < buflen - 32; ++t)
     n += snprintf(buf + n, buflen - n, " [c%x f%x w%d+%d]", q.st_cmask[t], q.st_fmask[t], q.st_woff[t], q.st_wbytes[t]);
   return n;
@@ -981,6 +1057,8 @@ int tc_halo_prepare(TcLayer& t, const ConvProblem* probs, const float* const* w_
   t.nclass = nclass;
   t.n_tile = prm.n_tile; t.n_tiles = prm.n_tiles; t.k_chunks = prm.k_chunks; t.nsplit = nsplit;
   t.th = kTileH; t.tw = kTileW; t.tb = 1; t.stages = prm.sa; t.smem_bytes = plan->smem_bytes;
+  t.ksplit = prm.ksplit;
+  t.splitk_bytes = (prm.ksplit > 1) ? (size_t)prm.ksplit * p.B * p.Hfull * p.Wfull * ((p.Cout + 3) / 4 * 4) * sizeof(float) : 0;
   return DEMON_OK;
 }
 
@@ -1024,21 +1102,42 @@ int conv_tc_halo_launch(const TcLayer& t, const ConvProblem* probs, cudaStream_t
   if (!ds.err_dev) return fail(DEMON_E_CUDA, "tcgen05 path: no error flag on device %d", ds.device);
   prm.err = ds.err_dev;
   prm.timing = g_timing_dev;
-  const int grid = std::min(prm.total_tiles, ds.sms);
+  const int cpitch = (prm.Cout + 3) / 4 * 4;
+  const long long npix = (long long)prm.B * prm.Hfull * prm.Wfull;
+  float* const final_out = prm.out;
+  const int final_pitch = prm.out_pitch;
+  if (prm.ksplit > 1) {   // partial sums into the caller's scratch, bias and activation in the second pass
+    if (!probs[0].partial) return fail(DEMON_E_STATE, "conv_tc_halo: split-K layer launched without a scratch buffer");
+    prm.out = probs[0].partial;
+    prm.out_pitch = cpitch;
+    prm.part_stride = npix * cpitch;
+    prm.bias = nullptr;
+    prm.leaky = 0;
+  }
+  const int grid = std::min(prm.total_items, ds.sms);
   const int threads = 32 * (2 + 4 * prm.ngroups + 4 + 1);
+  int rc;
   if (prm.per_tap) {
-    if (prm.mode == 0) return launch_variant<true, false, 0>(plan, prm, grid, threads, stream);
-    if (prm.mode == 1) return launch_variant<true, false, 1>(plan, prm, grid, threads, stream);
-    return launch_variant<true, false, 2>(plan, prm, grid, threads, stream);
+    if (prm.mode == 0) rc = launch_variant<true, false, 0>(plan, prm, grid, threads, stream);
+    else if (prm.mode == 1) rc = launch_variant<true, false, 1>(plan, prm, grid, threads, stream);
+    else rc = launch_variant<true, false, 2>(plan, prm, grid, threads, stream);
+  } else if (prm.cin8) {
+    if (prm.mode == 0) rc = launch_variant<false, true, 0>(plan, prm, grid, threads, stream);
+    else if (prm.mode == 1) rc = launch_variant<false, true, 1>(plan, prm, grid, threads, stream);
+    else rc = launch_variant<false, true, 2>(plan, prm, grid, threads, stream);
+  } else {
+    if (prm.mode == 0) rc = launch_variant<false, false, 0>(plan, prm, grid, threads, stream);
+    else if (prm.mode == 1) rc = launch_variant<false, false, 1>(plan, prm, grid, threads, stream);
+    else rc = launch_variant<false, false, 2>(plan, prm, grid, threads, stream);
   }
-  if (prm.cin8) {
-    if (prm.mode == 0) return launch_variant<false, true, 0>(plan, prm, grid, threads, stream);
-    if (prm.mode == 1) return launch_variant<false, true, 1>(plan, prm, grid, threads, stream);
-    return launch_variant<false, true, 2>(plan, prm, grid, threads, stream);
-  }
-  if (prm.mode == 0) return launch_variant<false, false, 0>(plan, prm, grid, threads, stream);
-  if (prm.mode == 1) return launch_variant<false, false, 1>(plan, prm, grid, threads, stream);
-  return launch_variant<false, false, 2>(plan, prm, grid, threads, stream);
+  if (rc != DEMON_OK || prm.ksplit == 1) return rc;
+  const long long total = npix * (cpitch / 4);
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ds.sms * 8);
+  cudaError_t le = launch_pdl(halo_splitk_reduce_kernel, dim3(blocks), dim3(256), 0, stream, (const float*)probs[0].partial, prm.part_stride,
+                              prm.ksplit, final_out, final_pitch, cpitch, prm.Cout, npix, plan->prm.bias, plan->prm.leaky);
+  if (le != cudaSuccess) return fail(DEMON_E_CUDA, "halo_splitk_reduce launch: %s", cudaGetErrorString(le));
+  DEMON_LAUNCH_CHECK();
+  return DEMON_OK;
 }
 
 }  // namespace demon

@@ -532,6 +532,63 @@ __global__ void __launch_bounds__(128) sig_kernel(const T* __restrict__ in, T* _
   o[hw] = gy;
 }
 
+// float fast path: FOUR consecutive pixels per thread (W a multiple of 4, 16-byte aligned pointers, fewer than 2^31
+// elements).  The centre row and the row y + d are read as float4; the x neighbours x + d .. x + d + 3 come from the one or
+// two aligned groups that hold them.  Per pixel and delta the SAME sequence of IEEE operations as sig_kernel
+// (scaleinvariantgradient.cc:148-195): the ten divisions per pixel are what bounds the op (profiles/r02_ncu_ops.md).
+__global__ void __launch_bounds__(128) sig_v4_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int zbase,
+                                                    SigParams<float> prm) {
+  const int x = (blockIdx.x * 128 + threadIdx.x) * 4;
+  const int y = blockIdx.y;
+  const int z = zbase + blockIdx.z;
+  if (x >= W) return;
+  const int hw = H * W;
+  const float* p = in + z * hw;
+  const float* row = p + y * W;
+  const float4 c4 = __ldg(reinterpret_cast<const float4*>(row + x));
+  const float v0[4] = {c4.x, c4.y, c4.z, c4.w};
+  float gx[4] = {0.f, 0.f, 0.f, 0.f}, gy[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = 0; c < prm.num; ++c) {
+    const int d = prm.deltas[c];
+    const float wgt = prm.weights[c];
+    float vy[4] = {v0[0], v0[1], v0[2], v0[3]}, vx[4] = {v0[0], v0[1], v0[2], v0[3]};
+    if (y + d >= 0 && y + d < H) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(p + (y + d) * W + x));
+      vy[0] = t.x; vy[1] = t.y; vy[2] = t.z; vy[3] = t.w;
+    }
+    const int b = x + d;                       // first x neighbour
+    const int g0 = b & ~3, r = b - g0;         // aligned group that holds it, offset inside (arithmetic shift: fine for b < 0)
+    float g[8];
+    {
+      const bool in0 = g0 >= 0 && g0 < W, in1 = r != 0 && g0 + 4 >= 0 && g0 + 4 < W;
+      const float4 a = in0 ? __ldg(reinterpret_cast<const float4*>(row + g0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 e = in1 ? __ldg(reinterpret_cast<const float4*>(row + g0 + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = e.x; g[5] = e.y; g[6] = e.z; g[7] = e.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int xn = b + k;
+      if (xn >= 0 && xn < W) vx[k] = (r == 0) ? g[k] : (r == 1) ? g[k + 1] : (r == 2) ? g[k + 2] : g[k + 3];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      gx[k] = fadd(gx[k], fdiv(fmul(wgt, fsub(vx[k], v0[k])), fadd(fadd(tabs(v0[k]), tabs(vx[k])), prm.eps)));
+      gy[k] = fadd(gy[k], fdiv(fmul(wgt, fsub(vy[k], v0[k])), fadd(fadd(tabs(v0[k]), tabs(vy[k])), prm.eps)));
+    }
+  }
+  float* o = out + z * 2 * hw + y * W + x;
+  *reinterpret_cast<float4*>(o) = make_float4(gx[0], gx[1], gx[2], gx[3]);
+  *reinterpret_cast<float4*>(o + hw) = make_float4(gy[0], gy[1], gy[2], gy[3]);
+}
+
+template <class T>
+static bool sig_fast(const T*, T*, int, int, int, int, const SigParams<T>&, cudaStream_t) { return false; }
+template <>
+bool sig_fast<float>(const float* in, float* out, int h, int w, int z0, int zn, const SigParams<float>& prm, cudaStream_t s) {
+  sig_v4_kernel<<<dim3(ceil_div(w / 4, 128), h, zn), 128, 0, s>>>(in, out, h, w, z0, prm);
+  return true;
+}
+
 template <class T>
 static int sig_launch(const T* in, T* out, int64_t z, int h, int w, const int* deltas, const T* weights, int num, T eps,
                       void* stream) {
@@ -545,8 +602,14 @@ static int sig_launch(const T* in, T* out, int64_t z, int h, int w, const int* d
   prm.num = num;
   prm.eps = eps;
   for (int i = 0; i < 16; ++i) { prm.deltas[i] = i < num ? deltas[i] : 0; prm.weights[i] = i < num ? weights[i] : (T)0; }
+  const bool fast = sizeof(T) == 4 && (w & 3) == 0 && w >= 128 && z * 2 * h * w < (1ll << 31) &&
+                    ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
   for (int64_t z0 = 0; z0 < z; z0 += 32768) {
     int zn = (int)((z - z0 < 32768) ? (z - z0) : 32768);
+    if (fast && sig_fast<T>(in, out, h, w, (int)z0, zn, prm, (cudaStream_t)stream)) {
+      DEMON_LAUNCH_CHECK();
+      continue;
+    }
     sig_kernel<T><<<dim3(ceil_div(w, 128), h, zn), 128, 0, (cudaStream_t)stream>>>(in, out, h, w, (int)z0, prm);
     DEMON_LAUNCH_CHECK();
   }

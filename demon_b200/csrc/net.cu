@@ -99,6 +99,7 @@ struct demon_net {
   std::vector<int64_t> prof_calls;
 
   // named buffers
+  float* tc_scratch = nullptr;   // partial sums of the split-K tensor-core layers (conv_tc_halo.cu), sized at finalize
   Buf *cat2_f2, *cat2_d2;   // conv2 || conv2_extra_inputs of netFlow2 / netDM2: their conv2 half is loop invariant (see pipeline_body)
   Buf *img8, *i22, *i22_half, *c1y, *c1, *c2y, *cat2, *extra_in, *exy, *c21y, *concat2, *c3y, *c3, *c31y, *concat3, *c4y, *c4,
       *c41y, *concat4, *c5y, *c5, *c51y, *c51, *pf5a, *pf5, *p2a, *flowconf2, *dn2, *mc1, *fc1, *fc2, *motion;
@@ -151,6 +152,9 @@ void build_trunk(demon_net* n, const std::string& s, bool flow, bool iterative) 
   if (!(flow && !iterative)) {
     const int extra = flow ? 9 : (iterative ? 8 : 7);
     n->add_sep(s + "conv2_extra_inputs", 3, 1, n->extra_in, 0, extra, n->exy, 32, cat2, 32, 32);
+    // the 7 / 8 / 9 real channels sit in a 32-channel (128-byte) pixel whose other channels are zero and carry zero weights:
+    // one K = 32 chunk of the tcgen05 halo kernel (3 steps per tile) instead of the fp32 SIMT kernel (0.10 -> 0.02 ms per launch)
+    n->by_name[s + "conv2_extra_inputsy"]->cin_buf = 32;
   }
   n->add_sep(s + "conv2_1", 3, 1, cat2, 0, 64, n->c21y, 64, n->concat2, 64, 64);
   n->add_sep(s + "conv3", 5, 2, n->concat2, 64, 64, n->c3y, 128, n->c3, 0, 128);
@@ -170,7 +174,7 @@ void build_flow_block(demon_net* n, const std::string& scope, bool iterative) {
   n->add_layer(s + "upsample_flow5to4/upconv", L_DECONV, n->pf5, 0, 4, n->concat4, 512, 2, 4, 4, 2, 2, false);
   n->add_layer(s + "refine4/upconv", L_DECONV, n->c51, 0, 512, n->concat4, 0, 256, 4, 4, 2, 2, true);
   Layer* r3 = n->add_layer(s + "refine3/upconv", L_DECONV, n->concat4, 0, 514, n->concat3, 0, 128, 4, 4, 2, 2, true);
-  r3->cin_buf = 544;   // channels 514..543 of concat4 are never written (zero) and carry zero weights
+  r3->cin_buf = 576;   // channels 514..575 of concat4 are never written (zero) and carry zero weights; 18 chunks (not 17) so that the K loop can be split
   n->add_layer(s + "refine2/upconv", L_DECONV, n->concat3, 0, 256, n->concat2, 0, 64, 4, 4, 2, 2, true);
   n->add_layer(s + "predict_flow2/conv1", L_CONV, n->concat2, 0, 128, n->p2a, 0, 24, 3, 3, 1, 1, true);
   n->add_layer(s + "predict_flow2/conv2", L_CONV, n->p2a, 0, 24, n->flowconf2, 0, 4, 3, 3, 1, 1, false);
@@ -220,7 +224,7 @@ void build_plan(demon_net* n) {
   n->cat2 = n->add_buf(48, 64, 64);
   n->cat2_f2 = n->add_buf(48, 64, 64);
   n->cat2_d2 = n->add_buf(48, 64, 64);
-  n->extra_in = n->add_buf(48, 64, 12);
+  n->extra_in = n->add_buf(48, 64, 32);   // 12 channels written at most (flow_extra_kernel), the rest stays zero
   n->exy = n->add_buf(48, 64, 32);
   n->c21y = n->add_buf(48, 64, 64);
   n->concat2 = n->add_buf(48, 64, 128);
@@ -231,7 +235,7 @@ void build_plan(demon_net* n) {
   n->c4y = n->add_buf(12, 32, 256);
   n->c4 = n->add_buf(12, 16, 256);
   n->c41y = n->add_buf(12, 16, 256);
-  n->concat4 = n->add_buf(12, 16, 544);   // 512 + 2 (upsampled flow) padded to a multiple of 32 for the tcgen05 path
+  n->concat4 = n->add_buf(12, 16, 576);   // 512 + 2 (upsampled flow) padded to 18 chunks of 32 channels for the tcgen05 path (18 = 2 x 3 x 3: split-K)
   n->c5y = n->add_buf(6, 16, 512);
   n->c5 = n->add_buf(6, 8, 512);
   n->c51y = n->add_buf(6, 8, 512);
@@ -383,10 +387,13 @@ int build_problems(const Layer& l, int B, ConvProblem* out) {
   return 4;
 }
 
-int run_layer(const Layer& l, int B, cudaStream_t stream, float* splitk_ws = nullptr) {
+int run_layer(const Layer& l, int B, cudaStream_t stream, float* splitk_ws = nullptr, float* tc_ws = nullptr) {
   ConvProblem probs[4];
   const int nclass = build_problems(l, B, probs);
-  if (l.use_tc) return l.tc.halo_plan ? conv_tc_halo_launch(l.tc, probs, stream) : conv_tc_launch(l.tc, probs, stream);
+  if (l.use_tc) {
+    probs[0].partial = tc_ws;   // scratch of the split-K tensor-core layers (the net's, so two nets in flight do not share it)
+    return l.tc.halo_plan ? conv_tc_halo_launch(l.tc, probs, stream) : conv_tc_launch(l.tc, probs, stream);
+  }
   for (int c = 0; c < nclass; ++c) {
     if (l.kind == L_DENSE && l.ksplit > 1 && splitk_ws) { probs[c].partial = splitk_ws; probs[c].ksplit = l.ksplit; }
     int rc = conv_simt_launch(probs[c], stream);
@@ -399,19 +406,19 @@ int run_layer_profiled(demon_net* n, int idx, cudaStream_t stream) {
   const Layer& l = *n->layers[idx];
   static const bool sync_layers = getenv("DEMON_SYNC_LAYERS") && atoi(getenv("DEMON_SYNC_LAYERS")) != 0;   // debugging aid
   if (sync_layers) {
-    int rc = run_layer(l, n->B, stream, n->splitk->p);
+    int rc = run_layer(l, n->B, stream, n->splitk->p, n->tc_scratch);
     cudaError_t e = cudaStreamSynchronize(stream);
     if (rc == DEMON_OK && e != cudaSuccess) return fail(DEMON_E_CUDA, "layer %s: %s", l.name.c_str(), cudaGetErrorString(e));
     return rc;
   }
-  if (!n->profiling) return run_layer(l, n->B, stream, n->splitk->p);
+  if (!n->profiling) return run_layer(l, n->B, stream, n->splitk->p, n->tc_scratch);
   if (n->prof_used + 2 > n->prof_events.size()) {
     const size_t old = n->prof_events.size();
     n->prof_events.resize(old + 1024);
     for (size_t i = old; i < n->prof_events.size(); ++i) DEMON_CHECK_CUDA(cudaEventCreate(&n->prof_events[i]));
   }
   DEMON_CHECK_CUDA(cudaEventRecord(n->prof_events[n->prof_used], stream));
-  int rc = run_layer(l, n->B, stream, n->splitk->p);
+  int rc = run_layer(l, n->B, stream, n->splitk->p, n->tc_scratch);
   DEMON_CHECK_CUDA(cudaEventRecord(n->prof_events[n->prof_used + 1], stream));
   n->prof_layer.push_back(idx);
   n->prof_used += 2;
@@ -488,7 +495,8 @@ __global__ void __launch_bounds__(128) median_planes_kernel(const float* __restr
 // zero where |flow| >= 1 or NaN -> warp2d(image2_2, normalized, 'value') -> NHWC12
 // [warped(3), flow(2), depth(1), normal(3), 0, 0, 0].  dn2 = [depth, normal] NHWC4, motion [B,8] = rot|trans|scale.
 __global__ void __launch_bounds__(256) flow_extra_kernel(const float* __restrict__ dn2, const float* __restrict__ motion,
-                                                        const float* __restrict__ image2_2, float* __restrict__ extra, int H, int W) {
+                                                        const float* __restrict__ image2_2, float* __restrict__ extra, int H, int W,
+                                                        int extra_pitch) {
   pdl_launch_dependents();   // common.cuh: programmatic dependent launch
   pdl_wait();
   __shared__ D2FCamera<float> cam;
@@ -519,7 +527,7 @@ __global__ void __launch_bounds__(256) flow_extra_kernel(const float* __restrict
     }
     wv[c] = r;
   }
-  float4* o = reinterpret_cast<float4*>(extra) + ((size_t)n * hw + i) * 3;
+  float4* o = reinterpret_cast<float4*>(extra + ((size_t)n * hw + i) * extra_pitch);
   o[0] = make_float4(wv[0], wv[1], wv[2], fx);
   o[1] = make_float4(fy, d.x, d.y, d.z);
   o[2] = make_float4(d.w, 0.f, 0.f, 0.f);
@@ -559,6 +567,9 @@ __global__ void __launch_bounds__(128) dm_extra_kernel(const float* __restrict__
   float* o = extra + ((size_t)n * hw + i) * extra_pitch;
   *reinterpret_cast<float4*>(o) = make_float4(wv[0], wv[1], wv[2], fc.x);
   *reinterpret_cast<float4*>(o + 4) = make_float4(fc.y, fc.z, fc.w, dff);
+  // channels 8..11 belong to the Flow block's record (normal z, 0, 0, 0): clear them, a stale NaN there would survive its
+  // zero weight (the buffer is shared by the two blocks; channels 12.. are never written by anybody)
+  if (extra_pitch >= 12) *reinterpret_cast<float4*>(o + 8) = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // refinement input (blocks_original.py:466-482): concat(image1, nearest-neighbour upsampled depth2) -> NHWC4
@@ -681,7 +692,7 @@ int run_flow_block(demon_net* n, const std::string& scope, bool iterative, cudaS
   int rc;
   if (head && (rc = run_range(n, p + "conv1y", p + "conv2x", s))) return rc;
   if (iterative) {
-    (void)launch_pdl(flow_extra_kernel, dim3(dim3(ceil_div(48 * 64, 256), n->B)), dim3(256), 0, s, n->dn2->p, n->motion->p, n->i22->p, n->extra_in->p, 48, 64);
+    (void)launch_pdl(flow_extra_kernel, dim3(dim3(ceil_div(48 * 64, 256), n->B)), dim3(256), 0, s, n->dn2->p, n->motion->p, n->i22->p, n->extra_in->p, 48, 64, n->extra_in->C);
     DEMON_LAUNCH_CHECK();
     if ((rc = run_range(n, p + "conv2_extra_inputsy", p + "conv2_extra_inputsx", s))) return rc;
   }
@@ -837,6 +848,16 @@ int demon_net_finalize(demon_net* n) {
         l.use_tc = true;
       }
     }
+  }
+  // scratch of the split-K tensor-core layers: the largest need, owned by the net
+  size_t need = 0;
+  for (auto& lp : n->layers)
+    if (lp->use_tc) need = std::max(need, lp->tc.splitk_bytes);
+  if (need) {
+    void* q = nullptr;
+    DEMON_CHECK_CUDA(cudaMalloc(&q, need));
+    n->dev_allocs.push_back(q);
+    n->tc_scratch = static_cast<float*>(q);
   }
   n->host_vars.clear();
   n->finalized = true;
@@ -1241,10 +1262,17 @@ static int standalone_conv(const float* in, float* out, int B, int H, int W, int
     if (rc) return rc;
     l.use_tc = true;
   }
+  float* tc_ws = nullptr;
+  if (l.use_tc && l.tc.splitk_bytes) {
+    void* q = nullptr;
+    if (cudaMalloc(&q, l.tc.splitk_bytes) != cudaSuccess) return fail(DEMON_E_CUDA, "conv test entry: scratch allocation failed");
+    tmp.dev_allocs.push_back(q);
+    tc_ws = static_cast<float*>(q);
+  }
   cudaEvent_t ev0, ev1;
   cudaEventCreate(&ev0); cudaEventCreate(&ev1);
   cudaEventRecord(ev0, (cudaStream_t)stream);
-  rc = run_layer(l, B, (cudaStream_t)stream);
+  rc = run_layer(l, B, (cudaStream_t)stream, nullptr, tc_ws);
   cudaEventRecord(ev1, (cudaStream_t)stream);
   cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
   float ms = -1.f;

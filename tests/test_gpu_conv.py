@@ -156,10 +156,30 @@ def test_tc_conv_3xtf32_is_fp32_grade(case):
     assert _lib.load().demon_debug_tc_timeouts() == 0
 
 
-# transposed convs: per-tap mode at low resolution (refine4/3/2 shapes, 17 chunks for the 544-channel concat), halo mode
-# on whole 16x8 tiles (refine0: four stacked classes of N = 32; refine1: four classes of N = 64, three-instruction mode)
+# transposed convs: per-tap mode at low resolution (refine4/3/2 shapes; 17 chunks: a prime K loop that cannot be split, 18 chunks:
+# the 576-channel concat4 of the pipeline, split-K at small batch), halo mode on whole 16x8 tiles (refine0: four stacked
+# classes of N = 32; refine1: four classes of N = 64, three-instruction mode)
 TC_DECONV_CASES = [(2, 6, 8, 512, 256), (1, 12, 16, 256, 128), (1, 24, 32, 128, 32), (2, 12, 16, 128, 64), (1, 12, 16, 544, 128),
+                   (1, 12, 16, 576, 128), (2, 12, 16, 576, 128),
                    (3, 24, 32, 256, 64), (1, 32, 16, 128, 32), (2, 16, 24, 128, 64), (1, 16, 8, 32, 16)]
+
+
+def test_split_k_plans_are_what_the_tests_exercise():
+    """The halo planner splits the K loop of layers with few tiles (low resolution, small batch); the cases below and in
+    TC_DECONV_CASES therefore run the two-pass path (partial sums + halo_splitk_reduce_kernel).  No device needed."""
+    import ctypes
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(4096)
+
+    def plan(B, H, W, Cin, Cout, kh, kw, sy, sx, deconv):
+        lib.demon_debug_describe_conv(B, H, W, Cin, Cin, Cout, Cout, kh, kw, sy, sx, deconv, X3TF32, buf, 4096)
+        return buf.value.decode()
+
+    assert "ksplit 8" in plan(2, 6, 8, 512, 256, 4, 4, 2, 2, 1)        # refine4 at batch 2: 4 tiles, 160 steps
+    assert "ksplit 1 " in plan(1, 12, 16, 544, 128, 4, 4, 2, 2, 1)     # 17 chunks: prime
+    assert "ksplit 1 " not in plan(1, 12, 16, 576, 128, 4, 4, 2, 2, 1)
+    assert "ksplit 1 " not in plan(3, 6, 8, 512, 24, 3, 3, 1, 1, 0)     # predict_flow5/conv1
+    assert "ksplit 1 " in plan(64, 48, 64, 128, 24, 3, 3, 1, 1, 0)      # plenty of tiles: no split
 
 
 @pytest.mark.parametrize("case", TC_DECONV_CASES)

@@ -91,9 +91,9 @@ def test_variable_table_agrees_with_python_table(sessions):
 def test_tensor_core_path_is_selected_for_the_big_layers(sessions):
     net = sessions["3xtf32"].net(1)
     for layer in ("netRefine/conv1_1", "netFlow1/conv3x", "netDM2/refine3/upconv", "netRefine/refine0/upconv", "netFlow1/conv1y",
-                  "netRefine/conv0"):
+                  "netRefine/conv0", "netDM1/conv2_extra_inputsy", "netFlow2/conv2_extra_inputsy"):   # (7..9 channels in a 32-channel pixel)
         assert net.uses_tensor_cores(layer), layer
-    for layer in ("netDM1/conv2_extra_inputsy", "netDM1/motion_fc1", "netRefine/predict_depth0/conv2"):
+    for layer in ("netDM1/motion_fc1", "netRefine/predict_depth0/conv2", "netFlow2/predict_flow2/conv2"):
         assert not net.uses_tensor_cores(layer), layer
     assert not sessions["fp32"].net(1).uses_tensor_cores("netRefine/conv1_1")
 

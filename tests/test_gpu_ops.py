@@ -272,6 +272,24 @@ def test_sig_matches_oracle(ops, dtype):
                           oops.scale_invariant_gradient(A4, [1, 2, 4], [1, 0.5, 0.25], 0.001))
 
 
+@pytest.mark.parametrize("shape", [(2, 1, 9, 128), (1, 3, 21, 256), (2, 7, 132)])
+def test_sig_vector_path_matches_oracle_bit_for_bit(ops, shape):
+    """float, W a multiple of 4 and >= 128: four pixels per thread, x neighbours taken out of aligned float4 groups.  Deltas of
+    every residue mod 4, negative ones, one wider than the image, zeros and NaNs in the input."""
+    rng = np.random.RandomState(sum(shape))
+    A = rng.uniform(-2, 2, shape).astype(np.float32)
+    A[..., 0, :5] = 0
+    A[..., 3, 17] = np.nan
+    deltas = [1, 2, 3, 4, 5, 8, 16, -1, -2, -4, -7, 127, 300]
+    weights = [1.0 / (1 + i) for i in range(len(deltas))]
+    g = ops.scale_invariant_gradient(A, deltas, weights, 0.001)
+    r = oops.scale_invariant_gradient(A, deltas, weights, 0.001)
+    assert g.shape == r.shape
+    assert np.array_equal(np.isnan(g), np.isnan(r))
+    m = ~np.isnan(r)
+    assert np.array_equal(g[m].view(np.uint32), r[m].view(np.uint32))
+
+
 @pytest.mark.parametrize("dtype", TYPES)
 def test_leaky_relu_matches_oracle(ops, dtype):
     rng = np.random.RandomState(17)

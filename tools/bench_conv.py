@@ -23,7 +23,7 @@ SHAPES = {
     "conv5_1y": ("conv", 64, 6, 8, 512, 512, 3, 1, 1, 1),
     "conv3x": ("conv", 64, 24, 64, 128, 128, 1, 5, 1, 2),
     "refine2_upconv": ("deconv", 64, 24, 32, 256, 64),
-    "refine3_upconv": ("deconv", 64, 12, 16, 544, 128),
+    "refine3_upconv": ("deconv", 64, 12, 16, 576, 128),   # netFlow2/refine3/upconv: the 514-channel concat4 padded to 18 chunks
     "refine4_upconv": ("deconv", 64, 6, 8, 512, 256),
     "conv2_1y": ("conv", 64, 48, 64, 64, 64, 3, 1, 1, 1),
     "conv4x": ("conv", 64, 12, 32, 256, 256, 1, 5, 1, 2),

@@ -13,7 +13,7 @@ SHAPES = [
     ("conv1y", 0, 192, 256, 8, 8, 32, 32, 9, 1, 2, 1), ("conv1x", 0, 96, 256, 32, 32, 32, 32, 1, 9, 1, 2),
     ("conv2y(32)", 0, 96, 128, 32, 32, 32, 64, 7, 1, 2, 1), ("conv2x(32)", 0, 48, 128, 32, 64, 32, 64, 1, 7, 1, 2),
     ("conv2y(64)", 0, 96, 128, 32, 32, 64, 64, 7, 1, 2, 1), ("conv2x(64)", 0, 48, 128, 64, 64, 64, 64, 1, 7, 1, 2),
-    ("extra_y", 0, 48, 64, 12, 12, 32, 32, 3, 1, 1, 1), ("extra_x", 0, 48, 64, 32, 32, 32, 64, 1, 3, 1, 1),
+    ("extra_y", 0, 48, 64, 32, 32, 32, 32, 3, 1, 1, 1), ("extra_x", 0, 48, 64, 32, 32, 32, 64, 1, 3, 1, 1),
     ("conv2_1y", 0, 48, 64, 64, 64, 64, 64, 3, 1, 1, 1), ("conv2_1x", 0, 48, 64, 64, 64, 64, 128, 1, 3, 1, 1),
     ("conv3y", 0, 48, 64, 64, 128, 128, 128, 5, 1, 2, 1), ("conv3x", 0, 24, 64, 128, 128, 128, 128, 1, 5, 1, 2),
     ("conv3_1y", 0, 24, 32, 128, 128, 128, 128, 3, 1, 1, 1), ("conv3_1x", 0, 24, 32, 128, 128, 128, 256, 1, 3, 1, 1),
