@@ -917,12 +917,15 @@ static bool halo_build(const ConvProblem* probs, int nclass, int nsplit, HaloPla
   prm.total_tiles = m_tiles * prm.n_tiles;
   // ---- split-K: layers with few tiles and a long K loop (the 6x8 / 12x16 levels; everything at batch 1) leave most SMs
   // idle and run their K loop serially.  Cost model in cycles: rounds of 148 items x (steps of an item x ~600 + ~3000 of
-  // prologue / epilogue), + ~12000 for the second pass; a split has to win 10 %.
+  // prologue / epilogue), + ~12000 for the second pass + the partial sums' trip through L2; a split has to win 10 %.
   prm.ksplit = 1;
   if (splitk_enabled() && !prm.cin8 && prm.k_chunks >= 4) {
+    // the partial sums travel to the second pass through L2 (~4000 B per cycle for write + read back): measured on
+    // netFlow2/refine3/upconv at batch 64 (25 MB of output), three slices win 8 %, not the 24 % the rounds alone promise
+    const long out_bytes = (long)p.B * p.Hfull * p.Wfull * ((p.Cout + 3) / 4 * 4) * 4;
     auto cost = [&](int ks) {
       const long items = (long)prm.total_tiles * ks;
-      return ((items + 147) / 148) * ((long)(prm.k_chunks / ks) * prm.nsteps * 600 + 3000) + (ks > 1 ? 12000 : 0);
+      return ((items + 147) / 148) * ((long)(prm.k_chunks / ks) * prm.nsteps * 600 + 3000) + (ks > 1 ? 12000 + ks * out_bytes * 2 / 4000 : 0);
     };
     long best = cost(1);
     for (int ks = 2; ks <= 8; ++ks) {

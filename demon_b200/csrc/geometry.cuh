@@ -178,8 +178,14 @@ __device__ void f2d_camera(F2DCamera& cam, const T* intrinsics, const T* rotatio
 // The reference calls Eigen's JacobiSVD in precision T on a heap-allocated dynamic matrix.  Here: Householder
 // QR in double -- backward stable, error cond(A) * 1e-16, so the result is the exact least-squares solution
 // to float output precision.
-// Rank deficiency shows up as a zero pivot -> non-finite X -> output 0, the same value the reference
+// EXACT rank deficiency shows up as a zero pivot -> non-finite X -> output 0, the same value the reference
 // produces through its minimum-norm solution (X.z = 0 fails `X.z() > 0`, flowtodepth.cc:464).
+// Deviation, stated plainly: for NUMERICALLY rank-deficient pixels (the flow within ~1e-7 relative of the
+// infinite-depth flow, cond(A) above ~1e7) the reference's float JacobiSVD drops the small singular value by Eigen's
+// rank rule and returns the minimum-norm X, i.e. a tiny inverse depth or 0; the QR below has no rank threshold and
+// returns the exact least-squares solution of the float inputs, a large |X.z| of either sign (depth 0 or a finite
+// noisy value).  Both are "depth unknown" answers; the reference's own tests (test_FlowToDepth2.py, 1e-4) do not
+// exercise such pixels and pass.
 __device__ __forceinline__ void lsq_4x3_qr(double X[3], double A[4][3], double b[4]) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) {

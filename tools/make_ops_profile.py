@@ -11,9 +11,9 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-ALG_MB = {"warp2d": 201.3, "depth_to_flow": 75.5, "flow_to_depth": 75.5, "median3x3": 94.4, "sig_kernel": 75.5, "leaky_relu": 151.0}
+ALG_MB = {"warp2d": 201.3, "depth_to_flow": 75.5, "flow_to_depth": 75.5, "median3x3": 94.4, "sig_": 75.5, "leaky_relu": 151.0}
 PIXELS = {"warp2d": 8 * 768 * 1024, "depth_to_flow": 8 * 768 * 1024, "flow_to_depth": 8 * 768 * 1024, "median3x3": 8 * 3 * 384 * 512,
-          "sig_kernel": 8 * 768 * 1024, "leaky_relu": 8 * 3 * 768 * 1024}
+          "sig_": 8 * 768 * 1024, "leaky_relu": 8 * 3 * 768 * 1024}
 
 
 def main():
@@ -25,7 +25,10 @@ def main():
             peak = float(json.load(open(p)).get("hbm_gbs", peak))
         except Exception:
             pass
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     ix = {h: i for i, h in enumerate(hdr)}

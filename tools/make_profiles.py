@@ -47,7 +47,10 @@ def launches(tag, path):
 
 
 def ncu_rep(tag, name, path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):   # already exported on the GPU box (`ncu -i rep --page raw --csv`): the reports themselves exceed gpurun's 64 MiB return limit
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
     d = {}
@@ -73,7 +76,7 @@ def main():
         if os.path.isfile(path):
             reps.append(ncu_rep(tag, name, path))
     if reps:
-        lines = ["# %s -- `ncu --set full --clock-control none --import-source on`, one launch per kernel/shape (batch 64)" % tag, ""]
+        lines = ["# %s -- `ncu --set full --clock-control none`, one launch per kernel/shape (batch 64)" % tag, ""]
         traffic = {}
         for name, d in reps:
             lines += ["## %s" % name, "", "kernel: `%s`" % d.get("Kernel Name", ("?", ""))[0][:120], "", "| metric | value | unit |", "|---|---|---|"]
