@@ -603,6 +603,29 @@ def main():
     dt = parallel.max_over_ranks(dt_local, dev)
     e2e = {"value": world * B * e2e_steps / dt, "unit": "pairs/s", "h2d_bytes_per_step": int(h_in[0].numel() * 4),
            "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": api}
+    # the same end to end from uint8 images (what examples/example.py loads): /255 - 0.5, pair concat and image2_2 on the
+    # device, a quarter of the host -> device bytes.  Extra information; `e2e` above stays on the fp32 inputs the CPU arm gets.
+    e2e_u8 = None
+    if world == 1:
+        g8 = torch.Generator().manual_seed(99)
+        h_u8 = [torch.randint(0, 256, (B, 2, 192, 256, 3), generator=g8, dtype=torch.uint8).pin_memory() for _ in range(NE)]
+
+        def e2e_u8_step(i):
+            k = i % NE
+            streams[k].synchronize()
+            pipes[k].forward_host_u8(h_u8[k], None, h_depth[k], h_rot[k], h_tr[k], streams[k], sync=False)
+        for i in range(3 * NE):
+            e2e_u8_step(i)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            e2e_u8_step(i)
+        torch.cuda.synchronize()
+        dt8 = time.perf_counter() - t0
+        _lib.check_errors()
+        e2e_u8 = {"value": B * e2e_steps / dt8, "unit": "pairs/s", "h2d_bytes_per_step": int(h_u8[0].numel()), "d2h_bytes_per_step": d2h,
+                  "steps": e2e_steps, "api": "demon_pipeline_forward_host_u8_async (C ABI) via DemonPipeline.forward_host_u8(sync=False): uint8 "
+                  "[B,2,192,256,3] images in pinned host memory, preprocessing on the device"}
 
     # ---- CPU side (rank 0): check of the last timed step against the oracle, and the CPU baseline at N=1 -------------
     cpu, check = None, None
@@ -645,12 +668,18 @@ def main():
                            "executed_flops_per_pair": alg_flops - 2.0 * hoisted_macs_per_pair(),
                            "flops_note": "value, algorithmic_tflops and roofline count the reference's algorithmic work; conv1/conv2 of the "
                                          "iterative nets are loop invariant and executed once per call (bit identical)"},
-                "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu, "check": check,
+                "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "e2e_u8": e2e_u8, "roofline": roofline, "cpu_baseline": cpu, "check": check,
                 "gather_ms": gather_ms, "algorithmic_tflops": alg_flops * value / 1e12}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Leave without tearing NCCL down: the step graphs hold captured NCCL kernels, and destroy_process_group() on a
+        # communicator that instantiated CUDA graphs still reference has been seen to hang after the result line was printed
+        # (2 GPUs, torch 2.11 / NCCL 2.28).  Everything is synchronised and flushed; the exit code is 0 on every rank.
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -883,6 +883,14 @@ static bool halo_build(const ConvProblem* probs, int nclass, int nsplit, HaloPla
     if (n_tile < 16 || nclass * n_tile + ring_cols > 512) return false;
     prm.mode = (nsplit == 1) ? 0 : 2;
     if (nsplit == 3 && n_tile <= 64 && nclass * 2 * n_tile + ring_cols <= 512) prm.mode = 1;
+    // experiments (A/B): three-instruction mode where the stacked accumulators cost the double buffering (four classes of
+    // N = 32: netRefine/refine0) or where the epilogue is the bound (8-channel layers: half the TMEM reads, no add)
+    {
+      static const int exp_mode2 = []() { const char* e = getenv("DEMON_TC_MODE2"); return e ? atoi(e) : 0; }();   // bit 0: multi-class, bit 1: cin8
+      if (prm.mode == 1 && (((exp_mode2 & 1) && nclass == 4 && 2 * nclass * 2 * n_tile + ring_cols > 512 && 2 * nclass * n_tile + ring_cols <= 512) ||
+                            ((exp_mode2 & 2) && prm.cin8)))
+        prm.mode = 2;
+    }
     prm.n_tile = n_tile;
     prm.acc_w = (prm.mode == 1 ? 2 : 1) * n_tile;
     prm.nbuf = (2 * nclass * prm.acc_w + ring_cols <= 512) ? 2 : 1;
