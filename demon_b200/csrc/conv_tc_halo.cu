@@ -883,12 +883,14 @@ static bool halo_build(const ConvProblem* probs, int nclass, int nsplit, HaloPla
     if (n_tile < 16 || nclass * n_tile + ring_cols > 512) return false;
     prm.mode = (nsplit == 1) ? 0 : 2;
     if (nsplit == 3 && n_tile <= 64 && nclass * 2 * n_tile + ring_cols <= 512) prm.mode = 1;
-    // experiments (A/B): three-instruction mode where the stacked accumulators cost the double buffering (four classes of
-    // N = 32: netRefine/refine0) or where the epilogue is the bound (8-channel layers: half the TMEM reads, no add)
+    // Three-instruction mode instead of the stacked one where the stacked accumulators would cost the double buffering (four
+    // classes of N = 32, netRefine/refine0: 0.626 -> 0.585 ms, the epilogue of tile i overlaps tile i + 1 again) and where the
+    // epilogue is the bound (8-channel layers: half the TMEM reads and no add per tile, conv1y 0.124 -> 0.119 ms).
+    // DEMON_TC_MODE2=0 switches both off (A/B), bit 0 = multi-class, bit 1 = 8-channel.
     {
-      static const int exp_mode2 = []() { const char* e = getenv("DEMON_TC_MODE2"); return e ? atoi(e) : 0; }();   // bit 0: multi-class, bit 1: cin8
-      if (prm.mode == 1 && (((exp_mode2 & 1) && nclass == 4 && 2 * nclass * 2 * n_tile + ring_cols > 512 && 2 * nclass * n_tile + ring_cols <= 512) ||
-                            ((exp_mode2 & 2) && prm.cin8)))
+      static const int mode2 = []() { const char* e = getenv("DEMON_TC_MODE2"); return e ? atoi(e) : 3; }();
+      if (prm.mode == 1 && (((mode2 & 1) && nclass == 4 && 2 * nclass * 2 * n_tile + ring_cols > 512 && 2 * nclass * n_tile + ring_cols <= 512) ||
+                            ((mode2 & 2) && prm.cin8)))
         prm.mode = 2;
     }
     prm.n_tile = n_tile;
