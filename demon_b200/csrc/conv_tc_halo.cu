@@ -100,6 +100,8 @@ struct HaloParams {
   int sa;               // A (halo, shared memory) stages
   int w_chunk_bytes;    // weight bytes of one (n tile, chunk): sum of st_wbytes
   int w_stage_bytes;    // weight ring slot = the largest step
+  int w_region_bytes;   // shared memory of the weights: kRing slots, or the whole layer when resident
+  int w_resident;       // 1: ALL weight blocks of the (single) n tile live in shared memory for the whole kernel, loaded once
   int cls_bytes;        // one class block: [W_hi ; W_lo] (3xTF32) or W alone
   int n_tile, nsplit, tmem_cols;
   int nbuf;             // accumulator buffers (2 = epilogue overlaps the next tile; 1 when TMEM is short)
@@ -174,6 +176,7 @@ struct MmaCtx {
   uint32_t t_ring;            // TMEM address of ring slot 0 (A_hi at +0, A_lo at +32)
   uint32_t w_ring;            // shared-memory address of weight slot 0
   uint32_t w_stage_bytes, cls_bytes;
+  uint32_t w_resident;        // weights resident: the block of step l of a tile is at w_ring + l * w_stage_bytes
   uint32_t n_tile, acc_w;
   uint32_t idesc, idesc2;
   int* err;
@@ -225,7 +228,7 @@ __device__ __forceinline__ void issue_block(const MmaCtx& c, uint32_t d, uint32_
 //   - ONE commit: frees the TMEM columns (stagers) and the weight slot (W producer)
 template <int MODE, int SLOT, bool MULTI>
 __device__ __forceinline__ bool mma_step(const MmaCtx& c, uint32_t d_base, uint32_t par, uint32_t npar, bool rdy, bool fresh, uint32_t cm,
-                                         uint32_t fm, long long& w_full) {
+                                         uint32_t fm, long long& w_full, int l) {
 #ifdef DEMON_TC_TIMING_FULL
   // diagnostic build: every wait bracketed by clock reads, and an event log of CTA 0's first 64 steps (tools/bench_conv.py prints it)
   if (c.evlog && c.ev_step < 64) { c.evlog[512 + c.ev_step] = clock64(); c.evlog[576 + c.ev_step] = rdy ? 1 : 0; }   // step entered, early probe result
@@ -239,7 +242,7 @@ __device__ __forceinline__ bool mma_step(const MmaCtx& c, uint32_t d_base, uint3
 #endif
   const bool next_rdy = mbar_test(c.full0 + 8 * ((SLOT + 1) & (kRing - 1)), npar);
   const uint32_t a_hi = c.t_ring + (uint32_t)(SLOT * 64);
-  uint32_t wb = c.w_ring + (uint32_t)SLOT * c.w_stage_bytes;
+  uint32_t wb = c.w_ring + (c.w_resident ? (uint32_t)l : (uint32_t)SLOT) * c.w_stage_bytes;
   if (!MULTI) {
     issue_block<MODE>(c, d_base, a_hi, wb, fresh);
   } else {
@@ -289,7 +292,7 @@ __device__ __forceinline__ void mma_main_loop(const HaloParams& p, const MmaCtx&
       fm = (l < nsteps) ? ((uint32_t)(fmasks >> (4 * t)) & 15u) : 0u;                                                     \
       if (++t == nsteps) t = 0;                                                                                           \
     }                                                                                                                     \
-    rdy = mma_step<MODE, SLOT, MULTI>(c, d_base, par, (SLOT == kRing - 1) ? (par ^ 1u) : par, rdy, l == 0, cm, fm, w_full); \
+    rdy = mma_step<MODE, SLOT, MULTI>(c, d_base, par, (SLOT == kRing - 1) ? (par ^ 1u) : par, rdy, l == 0, cm, fm, w_full, l); \
     if (++l == steps_per_tile) {                                                                                          \
       umma_commit(cfull_bar);   /* the tile's accumulators are complete once everything issued so far has retired */      \
       tile += gridDim.x;                                                                                                  \
@@ -318,7 +321,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   // bars: A_full[4], A_empty[4], full[4], free[4], accum_full[2], accum_empty[2]
-  __shared__ __align__(8) uint64_t bars[2 * kMaxAStages + 2 * kRing + 4];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxAStages + 2 * kRing + 4 + 1];   // (+ W_resident)
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
@@ -330,6 +333,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
   const uint32_t full0 = smem_u32(&bars[2 * kMaxAStages]), free0 = smem_u32(&bars[2 * kMaxAStages + kRing]);
   const uint32_t cfull0 = smem_u32(&bars[2 * kMaxAStages + 2 * kRing]);
   const uint32_t cempty0 = smem_u32(&bars[2 * kMaxAStages + 2 * kRing + 2]);
+  const uint32_t wres_bar = smem_u32(&bars[2 * kMaxAStages + 2 * kRing + 4]);
   const int a_stage_bytes = p.a_region_bytes;
   unsigned char* w_ring = smem + (size_t)p.sa * a_stage_bytes;
 
@@ -340,13 +344,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
       mbar_init(aempty0 + 8 * s, (uint32_t)p.aempty_count);
     }
     for (int s = 0; s < kRing; ++s) {
-      mbar_init(full0 + 8 * s, 4 + 1);   // the four warps of the stager group that owns the step + the W producer's expect_tx
+      mbar_init(full0 + 8 * s, p.w_resident ? 4 : 4 + 1);   // the four warps of the stager group that owns the step (+ the W producer's expect_tx)
       mbar_init(free0 + 8 * s, 1);       // the MMA thread's commit
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(cfull0 + 8 * s, 1);
       mbar_init(cempty0 + 8 * s, 4);
     }
+    mbar_init(wres_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), (uint32_t)p.tmem_cols);
@@ -406,7 +411,17 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
     // The copy's bytes complete on the step's `full` barrier (the one the stager group arrives on).  Both producers of a
     // slot wait for free[slot] of the previous round before they arrive for the next one, so all five arrivals and the
     // bytes of a step belong to the same barrier phase.
-    if (elect_one_sync()) {
+    const bool w_elected = elect_one_sync();
+    if (w_elected && p.w_resident) {
+      // Resident weights (narrow single-n-tile layers: the whole layer's packed weights are 24 .. 96 KB): a few large copies
+      // at the start instead of one 4 .. 8 KB cp.async.bulk per step.  The small copies of one SM execute one after the
+      // other at ~440 cycles each (event log in profiles/r02_ring_latency.md: a copy lands ~2900 cycles after it is issued
+      // with six ahead of it), and THAT is the ~440-cycle step of the narrow layers, whatever N and whatever the ring depth.
+      const uint32_t total = (uint32_t)(p.k_chunks * p.w_chunk_bytes);
+      mbar_expect_tx(wres_bar, total);
+      for (int kc = 0; kc < p.k_chunks; ++kc)
+        bulk_load(smem_u32(w_ring + (size_t)kc * p.w_chunk_bytes), p.w + (size_t)kc * p.w_chunk_bytes, (uint32_t)p.w_chunk_bytes, wres_bar);
+    } else if (w_elected) {
       int slot = 0;
       uint32_t use = 0;
       long long w_free = 0;
@@ -440,8 +455,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
       c.evlog = (timed && blockIdx.x == 0) ? p.timing + 160 * 16 : nullptr;
       c.ev_step = 0;
 #endif
+      c.w_resident = (uint32_t)p.w_resident;
       long long w_cempty = 0, w_full = 0;
       const long long t_begin = clock64();
+      if (p.w_resident) wait_t(wres_bar, 0u, p.err, w_full, false);
       if (p.nclass == 1) mma_main_loop<MODE, false>(p, c, tmem_base, acc_cols, cfull0, cempty0, w_cempty, w_full);
       else mma_main_loop<MODE, true>(p, c, tmem_base, acc_cols, cfull0, cempty0, w_cempty, w_full);
       if (timed) {
@@ -588,7 +605,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) conv_tc_halo_kernel(const __gr
     // then one float4 per lane and chunk.
     const int q = warp & 3;
     const int sub = lane >> 3, chunk = lane & 7;
-    const uint32_t stg = smem_u32(w_ring + (size_t)kRing * p.w_stage_bytes) + (uint32_t)(q * kEpiStageBytes);
+    const uint32_t stg = smem_u32(w_ring + (size_t)p.w_region_bytes) + (uint32_t)(q * kEpiStageBytes);
     int rowoff[8];          // element offset of row 4 i + sub of this warp's block inside the output tile
     uint32_t rowpos[8];     // its (yl, xl, nl) for the bounds test
 #pragma unroll
@@ -733,6 +750,11 @@ static int stager_groups() {
     return (v < 1 || v > kMaxGroups) ? 2 : v;
   }();
   return g;
+}
+
+static bool w_resident_enabled() {   // DEMON_W_RESIDENT=0: weights always through the 4-slot ring (A/B measurements)
+  static const bool v = []() { const char* e = getenv("DEMON_W_RESIDENT"); return !(e && e[0] == '0'); }();
+  return v;
 }
 
 static bool splitk_enabled() {   // DEMON_TC_SPLITK=0: never split the K loop of a tensor-core layer (A/B measurements)
@@ -913,11 +935,20 @@ static bool halo_build(const ConvProblem* probs, int nclass, int nsplit, HaloPla
     }
     prm.w_chunk_bytes = woff;
     prm.w_stage_bytes = wmax;
-    // shared memory: the weight ring, then up to 4 halo stages (at least 2)
-    const int rest = budget - kRing * wmax;
+    // shared memory: the weights (a ring of kRing slots, or the whole layer: see the W producer), then up to 4 halo stages
+    // (at least 2).  Resident: one n tile, one class, every step the same size, <= 96 KB in all and at least 2 A stages left.
+    const int w_total = prm.k_chunks * prm.w_chunk_bytes;
+    prm.w_resident = 0;
+    prm.w_region_bytes = kRing * wmax;
+    if (w_resident_enabled() && nclass == 1 && prm.n_tiles == 1 && w_total <= 96 * 1024 && wmax * prm.nsteps == prm.w_chunk_bytes &&
+        budget - w_total >= 2 * prm.a_region_bytes) {
+      prm.w_resident = 1;
+      prm.w_region_bytes = w_total;
+    }
+    const int rest = budget - prm.w_region_bytes;
     if (rest < 2 * prm.a_region_bytes) continue;   // next candidate: narrower steps / narrower N tile
     prm.sa = std::min(kMaxAStages, rest / prm.a_region_bytes);
-    plan.smem_bytes = prm.sa * prm.a_region_bytes + kRing * wmax + 4 * kEpiStageBytes + 1024;
+    plan.smem_bytes = prm.sa * prm.a_region_bytes + prm.w_region_bytes + 4 * kEpiStageBytes + 1024;
     found = true;
     break;
   }
@@ -929,7 +960,7 @@ static bool halo_build(const ConvProblem* probs, int nclass, int nsplit, HaloPla
   // idle and run their K loop serially.  Cost model in cycles: rounds of 148 items x (steps of an item x ~600 + ~3000 of
   // prologue / epilogue), + ~12000 for the second pass + the partial sums' trip through L2; a split has to win 10 %.
   prm.ksplit = 1;
-  if (splitk_enabled() && !prm.cin8 && prm.k_chunks >= 4) {
+  if (splitk_enabled() && !prm.cin8 && !prm.w_resident && prm.k_chunks >= 4) {
     // the partial sums travel to the second pass through L2 (~4000 B per cycle for write + read back): measured on
     // netFlow2/refine3/upconv at batch 64 (25 MB of output), three slices win 8 %, not the 24 % the rounds alone promise
     const long out_bytes = (long)p.B * p.Hfull * p.Wfull * ((p.Cout + 3) / 4 * 4) * 4;
@@ -1000,9 +1031,9 @@ int tc_halo_describe(const ConvProblem* probs, int nclass, int nsplit, char* buf
   HaloPlan plan;
   if (!halo_build(probs, nclass, nsplit, plan, false)) return snprintf(buf, buflen, "halo: unsupported");
   const HaloParams& q = plan.prm;
-  int n = snprintf(buf, buflen, "halo %s mode %d n_tile %d x%d nbuf %d tmem %d steps %d x %d chunks sa %d a_stage %d w_slot %d smem %d tiles %d groups %d ksplit %d |",
+  int n = snprintf(buf, buflen, "halo %s mode %d n_tile %d x%d nbuf %d tmem %d steps %d x %d chunks sa %d a_stage %d w_slot %d smem %d tiles %d groups %d ksplit %d wres %d |",
                    q.per_tap ? "per-tap" : (q.cin8 ? "cin8" : "halo"), q.mode, q.n_tile, q.n_tiles, q.nbuf, q.tmem_cols, q.nsteps, q.k_chunks, q.sa,
-                   q.a_region_bytes, q.w_stage_bytes, plan.smem_bytes, q.total_tiles, q.ngroups, q.ksplit);
+                   q.a_region_bytes, q.w_stage_bytes, plan.smem_bytes, q.total_tiles, q.ngroups, q.ksplit, q.w_resident);
   for (int t = 0; t < q.nsteps && n < buflen - 32; ++t)
     n += snprintf(buf + n, buflen - n, " [c%x f%x w%d+%d]", q.st_cmask[t], q.st_fmask[t], q.st_woff[t], q.st_wbytes[t]);
   return n;
