@@ -24,6 +24,11 @@
 // (expect_tx), so the MMA thread polls ONE barrier per step; free[s] is ONE tcgen05.commit per step that releases the TMEM
 // columns to the stagers and the weight slot to the W producer at the same time.
 //
+// Narrow single-n-tile layers keep their whole packed weight set (<= 96 KB) RESIDENT in shared memory instead of streaming
+// one block per step through the ring: the small bulk copies of one SM execute one after the other at ~440 cycles each, which
+// capped those layers at ~440 cycles per step (profiles/r02_ring_latency.md).  Layers with few tiles split their K loop over
+// several work items (split-K, halo_splitk_reduce_kernel).
+//
 // The MMA thread is the pacemaker of the CTA (profiles/r01_wait_counters.txt: it never waits, it IS the critical path),
 // and what it pays for is its own dependent instruction stream: every value that travels from a vector register to the
 // uniform datapath (R2UR, VOTEU) in front of a UTCHMMA / UTCBAR costs tens of cycles.  The loop is therefore written so
