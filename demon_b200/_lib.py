@@ -36,6 +36,8 @@ PROTOTYPES = {
     "demon_replace_nonfinite_f64": [_P, _P, c_int64, c_double, _P],
     "demon_replace_nonfinite_grad_f32": [_P, _P, _P, c_int64, _P],
     "demon_replace_nonfinite_grad_f64": [_P, _P, _P, c_int64, _P],
+    "demon_depth_to_normals_f32": [_P, _P, _P, c_int64, c_int, c_int, c_int, _P],
+    "demon_depth_to_normals_f64": [_P, _P, _P, c_int64, c_int, c_int, c_int, _P],
     "demon_metric_workspace_bytes": [c_int, c_int64],
     "demon_depth_error_sums_f32": [_P, _P, c_int, c_int64, c_int, c_int, _P, _P, _P, _P, _P],
     "demon_depth_scale_factor": [_P, c_int, c_int, _P, _P],

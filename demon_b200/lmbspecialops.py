@@ -281,6 +281,33 @@ def replace_nonfinite(input, value=0.0):
     return _ret(out, was_np)
 
 
+def depth_to_normals(depth, intrinsics, inverse_depth=False):
+    """Normal map [N,3,H,W] (camera frame) of a depth map; leading dims collapse into N, `intrinsics` is [N,4] (or [4],
+    broadcast) normalised (fx, fy, cx, cy).  Border pixels and pixels next to a non-positive / non-finite depth are NaN
+    (depthtonormals.cc:29-238; shape rules :36-68)."""
+    dshape = _shp(depth)
+    if len(dshape) < 2:
+        raise ValueError("Shape must be at least rank 2 but is rank %d" % len(dshape))
+    kshape = _shp(intrinsics)
+    if len(kshape) < 1:
+        raise ValueError("Shape must be at least rank 1 but is rank 0")
+    if kshape[-1] != 4:
+        raise ValueError("Dimension must be 4 but is %d" % kshape[-1])
+    h, w = dshape[-2:]
+    n = _prod(dshape[:-2])
+    d, was_np = _as_cuda(depth)
+    k, _ = _as_cuda(intrinsics, d.dtype)
+    k = k.reshape(-1, 4)
+    if k.shape[0] == 1 and n != 1:
+        k = k.expand(n, 4)
+    if k.shape[0] != n:
+        raise ValueError("Dimensions must be equal: %d depth maps, %d intrinsics" % (n, k.shape[0]))
+    k = k.contiguous()
+    out = torch.empty((n, 3, h, w), dtype=d.dtype, device=d.device)
+    _call("demon_depth_to_normals" + _sfx(d), d.data_ptr(), k.data_ptr(), out.data_ptr(), n, h, w, int(bool(inverse_depth)), _stream())
+    return _ret(out, was_np)
+
+
 def replace_nonfinite_grad(gradients, input):
     """ReplaceNonfiniteGrad (replacenonfinite.cc:97-168): zero gradient where the input was not finite."""
     x, was_np = _as_cuda(input)

@@ -112,6 +112,10 @@ int demon_replace_nonfinite_f32(const float* input, float* output, int64_t size,
 int demon_replace_nonfinite_f64(const double* input, double* output, int64_t size, double value, void* stream);
 int demon_replace_nonfinite_grad_f32(const float* gradients, const float* input, float* output, int64_t size, void* stream);
 int demon_replace_nonfinite_grad_f64(const double* gradients, const double* input, double* output, int64_t size, void* stream);
+/* Replaces DepthToNormalsOp (depthtonormals.cc:117-238): depth [z,h,w] (inverse depth if inverse_depth != 0), intrinsics [z,4]
+ * normalised (fx, fy, cx, cy) -> normals [z,3,h,w] in the camera frame; NaN on the border and next to invalid depths */
+int demon_depth_to_normals_f32(const float* depth, const float* intrinsics, float* output, int64_t z, int h, int w, int inverse_depth, void* stream);
+int demon_depth_to_normals_f64(const double* depth, const double* intrinsics, double* output, int64_t z, int h, int w, int inverse_depth, void* stream);
 
 /* ------------------------------------------------------------------------
  * Evaluation metrics on the device (python/depthmotionnet/evaluation/metrics.py).

@@ -348,3 +348,82 @@ void FN(oracle_scale_invariant_gradient)(T* out, const T* in, int x_size, int y_
       }
   }
 }
+
+/* ------------------------------------------------------------------------
+ * depth_to_normals --
+ *   lmbspecialops/src/depthtonormals.cc:147-238 (depthtonormals_cpu), compute3dPoint :95-101
+ * depth [z][y][x], intrinsics [z][4] -> out [z][3][y][x]; border pixels and pixels with a
+ * non-positive / non-finite depth among their 4-neighbourhood are NaN.
+ * Eigen pieces restated (Eigen 3.3, THIRD PARTY, absent here):
+ *   Matrix3::inverse()   Eigen/src/LU/InverseImpl.h compute_inverse<.,.,3>: cofactors of column 0,
+ *                        det = (c0*m00 + c1*m10) + c2*m20, every entry = cofactor * (1/det)
+ *   cross(), normalize() (z = squaredNorm(); if (z > 0) v /= sqrt(z)), left-to-right sums
+ * ---------------------------------------------------------------------- */
+static void FN(d2n_point_)(T p[3], int x, int y, T depth, T i00, T i02, T i11, T i12)
+{
+  p[0] = ((x + (T)0.5)*i00 + i02)*depth;
+  p[1] = ((y + (T)0.5)*i11 + i12)*depth;
+  p[2] = depth;
+}
+static void FN(d2n_cross_)(T r[3], const T a[3], const T b[3])
+{
+  r[0] = a[1]*b[2] - a[2]*b[1];
+  r[1] = a[2]*b[0] - a[0]*b[2];
+  r[2] = a[0]*b[1] - a[1]*b[0];
+}
+static void FN(d2n_normalize_)(T v[3])
+{
+  const T z = (v[0]*v[0] + v[1]*v[1]) + v[2]*v[2];
+  if (z > (T)0) {
+    const T n = FN(sqrt_)(z);
+    v[0] = v[0]/n; v[1] = v[1]/n; v[2] = v[2]/n;
+  }
+}
+
+void FN(oracle_depth_to_normals)(T* out, const T* depth, const T* intrinsics, int x_size, int y_size, long z_size, int inverse_depth)
+{
+  const long xy_size = (long)x_size * y_size;
+  for (long z = 0; z < z_size; ++z) {
+    /* K = [[a,0,cx],[0,b,cy],[0,0,1]] */
+    const T a = intrinsics[4*z+0]*x_size, b = intrinsics[4*z+1]*y_size, cx = intrinsics[4*z+2]*x_size, cy = intrinsics[4*z+3]*y_size;
+    const T c0 = b*(T)1 - cy*(T)0;
+    const T c1 = (T)0*cx - (T)1*(T)0;
+    const T c2 = (T)0*cy - cx*b;
+    const T det = (c0*a + c1*(T)0) + c2*(T)0;
+    const T invdet = (T)1/det;
+    const T i00 = c0*invdet, i02 = c2*invdet;
+    const T i11 = ((T)1*a - (T)0*cx)*invdet;
+    const T i12 = (cx*(T)0 - a*cy)*invdet;
+    const T* dm = depth + z*xy_size;
+    T* normal = out + 3*z*xy_size;
+    for (int y = 0; y < y_size; ++y)
+      for (int x = 0; x < x_size; ++x) {
+        T n0 = FN(nan_)(), n1 = n0, n2 = n0;
+        if (!(x == 0 || y == 0 || x == x_size-1 || y == y_size-1)) {
+          T d = dm[(long)y*x_size + x], d_y0 = dm[(long)(y-1)*x_size + x], d_x0 = dm[(long)y*x_size + x-1];
+          T d_y1 = dm[(long)(y+1)*x_size + x], d_x1 = dm[(long)y*x_size + x+1];
+          if (inverse_depth) { d = 1/d; d_y0 = 1/d_y0; d_x0 = 1/d_x0; d_y1 = 1/d_y1; d_x1 = 1/d_x1; }
+          if (!(d <= 0 || !FN(isfinite_)(d) || d_y0 <= 0 || !FN(isfinite_)(d_y0) || d_x0 <= 0 || !FN(isfinite_)(d_x0) ||
+                d_y1 <= 0 || !FN(isfinite_)(d_y1) || d_x1 <= 0 || !FN(isfinite_)(d_x1))) {
+            T p[3], p_y0[3], p_x0[3], p_y1[3], p_x1[3], a1[3], b1[3], a0[3], b0[3], v1[3], v0[3], v[3];
+            FN(d2n_point_)(p, x, y, d, i00, i02, i11, i12);
+            FN(d2n_point_)(p_y0, x, y-1, d_y0, i00, i02, i11, i12);
+            FN(d2n_point_)(p_x0, x-1, y, d_x0, i00, i02, i11, i12);
+            FN(d2n_point_)(p_y1, x, y+1, d_y1, i00, i02, i11, i12);
+            FN(d2n_point_)(p_x1, x+1, y, d_x1, i00, i02, i11, i12);
+            for (int k = 0; k < 3; ++k) { a1[k] = p[k] - p_x1[k]; b1[k] = p_y1[k] - p[k]; a0[k] = p[k] - p_x0[k]; b0[k] = p_y0[k] - p[k]; }
+            FN(d2n_cross_)(v1, a1, b1);
+            FN(d2n_cross_)(v0, a0, b0);
+            FN(d2n_normalize_)(v1);
+            FN(d2n_normalize_)(v0);
+            for (int k = 0; k < 3; ++k) v[k] = v1[k] + v0[k];
+            FN(d2n_normalize_)(v);
+            n0 = v[0]; n1 = v[1]; n2 = v[2];
+          }
+        }
+        normal[(long)y*x_size + x] = n0;
+        normal[xy_size + (long)y*x_size + x] = n1;
+        normal[2*xy_size + (long)y*x_size + x] = n2;
+      }
+  }
+}

@@ -172,3 +172,19 @@ def scale_invariant_gradient(input, deltas=(1,), weights=(1.0,), epsilon=0.001):
     getattr(lib(), "oracle_scale_invariant_gradient" + sfx)(
         _p(out), _p(a), x, y, ctypes.c_long(z), _p(dl), _p(wt), len(dl), cty(np.float32(epsilon)))
     return out
+
+
+def depth_to_normals(depth, intrinsics, inverse_depth=False):
+    """depthtonormals.cc:147-238: normal map [N,3,H,W] of a depth map (leading dims collapse into N)."""
+    a = np.asarray(depth)
+    sfx, _ = _sfx(a.dtype)
+    a = _c(a, a.dtype)
+    if a.ndim < 2:
+        raise ValueError("rank must be at least 2")
+    y, x = a.shape[-2:]
+    z = int(np.prod(a.shape[:-2])) if a.ndim > 2 else 1
+    k = np.ascontiguousarray(np.broadcast_to(np.asarray(intrinsics, a.dtype).reshape(-1, 4), (z, 4)) if np.asarray(intrinsics).size == 4
+                             else np.asarray(intrinsics, a.dtype).reshape(z, 4))
+    out = np.empty((z, 3, y, x), a.dtype)
+    getattr(lib(), "oracle_depth_to_normals" + sfx)(_p(out), _p(a), _p(k), x, y, ctypes.c_long(z), int(bool(inverse_depth)))
+    return out

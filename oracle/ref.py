@@ -1,5 +1,5 @@
 """ORACLE (test infrastructure) -- the reference's OWN CPU op kernels, compiled here from
-/root/reference/lmbspecialops/src/{warp2d,median3x3downsample,scaleinvariantgradient,leakyrelu,depthtoflow,replacenonfinite}.cc
+/root/reference/lmbspecialops/src/{warp2d,median3x3downsample,scaleinvariantgradient,leakyrelu,depthtoflow,replacenonfinite,depthtonormals}.cc
 (unmodified, read where they lie) against the stub TensorFlow / Eigen headers in oracle/ref_stub/, as
 oracle/_ref/libref_ops.so (git-ignored, travels to the GPU box with the snapshot).
 
@@ -17,7 +17,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_ref", "libref_ops.so")
 REF_SRC = "/root/reference/lmbspecialops/src"
-_SOURCES = ["warp2d.cc", "median3x3downsample.cc", "scaleinvariantgradient.cc", "leakyrelu.cc", "depthtoflow.cc", "replacenonfinite.cc"]
+_SOURCES = ["warp2d.cc", "median3x3downsample.cc", "scaleinvariantgradient.cc", "leakyrelu.cc", "depthtoflow.cc", "replacenonfinite.cc", "depthtonormals.cc"]
 
 
 def build(force=False):
@@ -134,3 +134,8 @@ def replace_nonfinite(input, value=0.0):
 def replace_nonfinite_grad(gradients, input):
     """ReplaceNonfiniteGradOp::Compute, replacenonfinite.cc:123-150."""
     return run("ReplaceNonfiniteGrad", [gradients, input])
+
+
+def depth_to_normals(depth, intrinsics, inverse_depth=False):
+    """DepthToNormalsOp::Compute, depthtonormals.cc:117-238 (Matrix3::inverse, cross, normalize come from oracle/ref_stub/eigen_stub.h)."""
+    return run("DepthToNormals", [depth, intrinsics], "inverse_depth:b=%s" % _b(inverse_depth))

@@ -11,6 +11,8 @@
  *   - Matrix<T,3,1>::norm           sqrt of the left-to-right sum of squares
  *   - Quaternion::normalize         coeffs (x,y,z,w) /= sqrt(((x^2 + y^2) + z^2) + w^2)
  *   - Quaternion / AngleAxis::toRotationMatrix   the formulas of Eigen/src/Geometry/{Quaternion,AngleAxis}.h
+ *   - Matrix<T,3,3>::inverse        cofactors times 1/det, Eigen/src/LU/InverseImpl.h (depthtonormals.cc)
+ *   - Matrix<T,3,1>::cross / normalize   Eigen/src/Geometry/OrthoMethods.h, Eigen/src/Core/Dot.h
  * These are the same orders oracle/geometry_ops_impl.h uses, so a mismatch between _ref and the C oracle points at the
  * OP logic (index math, branches, loops), which is the part that comes from the reference's own source.
  */
@@ -114,6 +116,40 @@ class Matrix : public MatrixBase<Matrix<T, R, C> > {
   Matrix<T, N, C> topRows() const { Matrix<T, N, C> r; for (int j = 0; j < C; ++j) for (int i = 0; i < N; ++i) r(i, j) = (*this)(i, j); return r; }
   Matrix<T, C, R> transpose() const { Matrix<T, C, R> r; for (int j = 0; j < C; ++j) for (int i = 0; i < R; ++i) r(j, i) = (*this)(i, j); return r; }
   void setIdentity() { for (int j = 0; j < C; ++j) for (int i = 0; i < R; ++i) (*this)(i, j) = (i == j) ? T(1) : T(0); }
+  static Matrix Identity() { Matrix r; r.setIdentity(); return r; }
+  // 3x3 inverse, Eigen/src/LU/InverseImpl.h (compute_inverse<MatrixType, ResultType, 3> + compute_inverse_size3_helper) [order]:
+  // cofactor_3x3<i,j>(m) = m(i1,j1)*m(i2,j2) - m(i1,j2)*m(i2,j1) with i1=(i+1)%3, i2=(i+2)%3, j1=(j+1)%3, j2=(j+2)%3;
+  // det = (c00*m00 + c10*m10) + c20*m20; result(0,j) = cofactor<j,0> * invdet, result(1,j) = cofactor<j,1> * invdet, ...
+  Matrix inverse() const {
+    static_assert(R == 3 && C == 3, "only the fixed 3x3 inverse of depthtonormals.cc is restated");
+    const Matrix& m = *this;
+    auto cof = [&](int i, int j) { const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+                                   return m(i1, j1) * m(i2, j2) - m(i1, j2) * m(i2, j1); };
+    const T c0 = cof(0, 0), c1 = cof(1, 0), c2 = cof(2, 0);
+    const T det = (c0 * m(0, 0) + c1 * m(1, 0)) + c2 * m(2, 0);
+    const T invdet = T(1) / det;
+    Matrix r;
+    r(0, 0) = c0 * invdet; r(0, 1) = c1 * invdet; r(0, 2) = c2 * invdet;
+    r(1, 0) = cof(0, 1) * invdet; r(1, 1) = cof(1, 1) * invdet; r(1, 2) = cof(2, 1) * invdet;
+    r(2, 0) = cof(0, 2) * invdet; r(2, 1) = cof(1, 2) * invdet; r(2, 2) = cof(2, 2) * invdet;
+    return r;
+  }
+  // comma initialiser (`v << a, b, c;`): coefficients in storage order for vectors, row by row for matrices, like Eigen
+  struct CommaInit {
+    Matrix& m; int k;
+    CommaInit& operator,(const T& v) { m(k / C, k % C) = v; ++k; return *this; }
+  };
+  CommaInit operator<<(const T& v) { (*this)(0, 0) = v; return CommaInit{*this, 1}; }
+  template <class D>
+  Matrix cross(const MatrixBase<D>& o) const {   // MatrixBase::cross, Eigen/src/Geometry/OrthoMethods.h
+    static_assert(R * C == 3, "vector of size 3");
+    const D& b = o.derived();
+    return Matrix(d_[1] * b(2) - d_[2] * b(1), d_[2] * b(0) - d_[0] * b(2), d_[0] * b(1) - d_[1] * b(0));
+  }
+  void normalize() {   // MatrixBase::normalize (Eigen 3.3): z = squaredNorm(); if (z > 0) derived() /= sqrt(z)
+    const T z = squaredNorm();
+    if (z > T(0)) *this /= std::sqrt(z);
+  }
   void setZero() { for (int i = 0; i < R * C; ++i) d_[i] = T(0); }
   const T* data() const { return d_; }
   T* data() { return d_; }

@@ -76,3 +76,24 @@ def test_sig_autograd_matches_numeric_gradient(ops):
         fm = (ops.scale_invariant_gradient(xm, deltas, weights, eps) * w.cpu().numpy()).sum()
         num[idx] = (fp - fm) / (2 * h)
     np.testing.assert_allclose(analytic, num, rtol=1e-5, atol=1e-7)
+
+
+@needs_ref
+@pytest.mark.parametrize("dtype", TYPES)
+@pytest.mark.parametrize("inverse_depth", (False, True))
+def test_depth_to_normals_equals_reference_source(ops, dtype, inverse_depth):
+    """depth_to_normals (v2 losses / blocks): bit exact against depthtonormals.cc compiled in oracle/_ref, invalid depths and
+    borders included; [4] intrinsics broadcast; rank rules of the op's shape function."""
+    rng = np.random.RandomState(33)
+    d = rng.uniform(0.2, 4.0, (3, 1, 37, 141)).astype(dtype)
+    d[0, 0, 3, 4] = -1.0; d[0, 0, 8, 8] = 0.0; d[1, 0, 5, 5] = np.nan; d[2, 0, 9, 12] = np.inf
+    K = np.array([[0.89115971, 1.18821287, 0.5, 0.5], [1.1, 0.9, 0.45, 0.55], [0.7, 0.7, 0.5, 0.4]], dtype)
+    got = ops.depth_to_normals(d, K, inverse_depth)
+    want = ref.depth_to_normals(d, K, inverse_depth)
+    assert got.shape == (3, 3, 37, 141) and bits_equal(got, want)
+    one = ops.depth_to_normals(d[0, 0], K[0], inverse_depth)                      # rank 2 depth, [4] intrinsics
+    assert one.shape == (1, 3, 37, 141) and bits_equal(one, want[:1])
+    with pytest.raises(ValueError):
+        ops.depth_to_normals(np.ones(5, dtype), K[0])
+    with pytest.raises(ValueError):
+        ops.depth_to_normals(d, np.ones((3, 3), dtype))

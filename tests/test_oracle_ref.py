@@ -25,7 +25,7 @@ def bits_equal(a, b):
 def test_ref_registers_the_reference_kernels():
     ks = ref.kernels()
     for op in ("Warp2d", "Median3x3Downsample", "ScaleInvariantGradient", "ScaleInvariantGradientGrad", "LeakyReluLmb",
-               "LeakyReluLmbGrad", "DepthToFlow"):
+               "LeakyReluLmbGrad", "DepthToFlow", "DepthToNormals"):
         for t in ("float", "double"):
             assert "%s/CPU/%s" % (op, t) in ks
 
@@ -124,3 +124,27 @@ def test_depth_to_flow_equals_reference_source(dtype, rotation_format, inverse_d
     want = ref.depth_to_flow(depth, intrinsics, rot, t, rotation_format, inverse_depth, normalize_flow)
     assert got.shape == want.shape == (n, 2, 9, 12)
     assert bits_equal(got, want)
+
+
+@pytest.mark.parametrize("dtype", TYPES)
+@pytest.mark.parametrize("inverse_depth", (False, True))
+def test_depth_to_normals_equals_reference_source(dtype, inverse_depth):
+    """depthtonormals.cc compiled unmodified (Matrix3::inverse / cross / normalize from the stub) against the C restatement:
+    borders, non-positive, zero, NaN and infinite depths, two cameras."""
+    rng = np.random.RandomState(31)
+    d = rng.uniform(0.2, 4.0, (2, 1, 17, 23)).astype(dtype)
+    d[0, 0, 3, 4] = -1.0; d[0, 0, 8, 8] = 0.0; d[1, 0, 5, 5] = np.nan; d[1, 0, 9, 12] = np.inf; d[1, 0, 2, 20] = 1e-30
+    K = np.array([[0.89115971, 1.18821287, 0.5, 0.5], [1.1, 0.9, 0.45, 0.55]], dtype)
+    a, b = oops.depth_to_normals(d, K, inverse_depth), ref.depth_to_normals(d, K, inverse_depth)
+    assert a.shape == (2, 3, 17, 23) and bits_equal(a, b)
+    assert np.isnan(a[:, :, 0, :]).all() and np.isnan(a[:, :, :, -1]).all()          # border
+    ok = ~np.isnan(a[:, 0])
+    norms = np.sqrt((a ** 2).sum(axis=1))[ok]      # unit normals (a pixel whose two half-normals cancel stays at its tiny sum)
+    assert ok.sum() > 100 and (np.abs(norms - 1.0) < 1e-5).mean() > 0.98
+
+
+def test_depth_to_normals_of_a_fronto_parallel_plane_points_at_the_camera():
+    d = np.full((1, 9, 11), 2.5, np.float32)
+    n = oops.depth_to_normals(d, np.array([0.9, 1.2, 0.5, 0.5], np.float32))
+    inner = n[0, :, 1:-1, 1:-1]
+    assert np.allclose(inner[0], 0, atol=1e-6) and np.allclose(inner[1], 0, atol=1e-6) and np.allclose(np.abs(inner[2]), 1, atol=1e-6)
